@@ -1,0 +1,774 @@
+// bp_device.cuh -- device-side implementation of the gym_blocks env hot path for sm_100a.
+//
+// Everything here is written for one thread = one env with the whole env state in
+// registers; the kernels in bp_kernels.cu decide how envs are tiled over warps.
+// Arithmetic follows the BlockPhys v1 specification of DESIGN.md exactly (fp32,
+// every operation individually rounded: compile with -fmad=false), so integer
+// state is bit-exact and float state bit-identical against the CPU oracle.
+//
+// Reference functions implemented (paths relative to /root/reference/gym_blocks):
+//   envs/robot_env.py:57-82      step / reset
+//   envs/fetch_env.py:135-143    compute_reward
+//   envs/fetch_env.py:148-167    _step_callback (touch matrix)
+//   envs/fetch_env.py:170-185    _set_action
+//   envs/fetch_env.py:187-228    _get_obs (:567-621 Variation)
+//   envs/fetch_env.py:247-281    _reset_sim, _sample_goal, _is_success
+//   envs/fetch_env.py:328-336, 370-399, 448-517, 646-764, 777-787  spawn samplers
+#pragma once
+#include <cstdint>
+
+namespace bp {
+
+// ---------------------------------------------------------------- constants
+constexpr int kNSub = 20;            // tasks.py:16 n_substeps
+constexpr float kH = 0.002f;         // 2blocks.xml:4
+constexpr float kInvH = 500.0f;
+constexpr float kDt = 0.04f;         // fetch_env.py:190
+constexpr float kGH = 0.01962f;
+constexpr float kFr = 0.01962f;
+constexpr float kFrW = 0.9f;
+constexpr float kKW = 2500.0f;
+constexpr float kBW = 100.0f;
+constexpr float kKF = 288.46155f;
+constexpr float kBF = 9.615385f;
+constexpr float kQMax = 0.05f;
+constexpr float kCtrlMax = 0.2f;
+constexpr float kTblX = 1.3f, kTblY = 0.75f, kTblHX = 0.25f, kTblHY = 0.35f;
+constexpr float kHB = 0.025f, kTwoHB = 0.05f;
+constexpr float kZRest = 0.485f, kZFloor = 0.025f;
+constexpr float kFX = 0.0135f, kFY = 0.007f, kFZ = 0.0385f, kFY0 = 0.0079f, kFZOff = 0.02f;
+constexpr float kGZMin = 0.4785f;
+constexpr float kMargin = 0.001f;
+constexpr float kDepen = 0.0005f;
+constexpr float kVMax = 5.0f, kWMax = 60.0f;
+constexpr float kIInv = 2400.0f;
+constexpr float kPosScale = 0.05f;   // fetch_env.py:175
+constexpr float kWsXLo = 1.0f, kWsXHi = 1.6f, kWsYLo = 0.35f, kWsYHi = 1.15f, kWsZHi = 0.9f;
+constexpr float kGrip0X = 1.3419f, kGrip0Y = 0.7491f, kGrip0Z = 0.5347f;
+// spawn geometry, fetch_env.py:19-32
+constexpr float kMinBlockDist = 0.075f;
+constexpr float kTableX = 1.3f, kTableY = 0.75f, kTableW = 0.225f, kTableH = 0.325f;
+constexpr int kMaxSpawnAttempts = 10000;
+constexpr int kT = 50;               // __init__.py:10
+constexpr int kMaxObjs = 6;
+
+__host__ __device__ constexpr int pair_index(int o1, int o2) {  // o1 < o2
+    return o1 * (2 * kMaxObjs - o1 - 1) / 2 + (o2 - o1 - 1);
+}
+__host__ __device__ constexpr uint32_t pair_bit(int o1, int o2) { return 1u << pair_index(o1, o2); }
+
+// ---------------------------------------------------------------- per-env-id configuration
+// SURVEY.md section 8 table; colours from fetch_env.py:323-326,360-363,434-441,632-639,772-775
+// reduce to the goal masks P (pairs that must touch) and M (pairs that must never have touched).
+template <int ID> struct Cfg;
+template <> struct Cfg<0> { static constexpr int NB = 1, DIMO = 25, DIMG = 9;  static constexpr bool BG = false, VAR = false; static constexpr uint32_t P = pair_bit(0, 2), M = 0; };
+template <> struct Cfg<1> { static constexpr int NB = 2, DIMO = 40, DIMG = 16; static constexpr bool BG = false, VAR = false; static constexpr uint32_t P = pair_bit(2, 3), M = 0; };
+template <> struct Cfg<2> { static constexpr int NB = 4, DIMO = 70, DIMG = 36; static constexpr bool BG = false, VAR = false; static constexpr uint32_t P = pair_bit(1, 5), M = pair_bit(0, 5); };
+template <> struct Cfg<3> { static constexpr int NB = 2, DIMO = 40, DIMG = 16; static constexpr bool BG = true,  VAR = false; static constexpr uint32_t P = pair_bit(2, 3), M = 0; };
+template <> struct Cfg<4> { static constexpr int NB = 3, DIMO = 55, DIMG = 25; static constexpr bool BG = true,  VAR = false; static constexpr uint32_t P = pair_bit(2, 3), M = 0; };
+template <> struct Cfg<5> { static constexpr int NB = 3, DIMO = 55, DIMG = 25; static constexpr bool BG = true,  VAR = false; static constexpr uint32_t P = pair_bit(2, 3), M = 0; };
+template <> struct Cfg<6> { static constexpr int NB = 4, DIMO = 87, DIMG = 36; static constexpr bool BG = true,  VAR = true;  static constexpr uint32_t P = pair_bit(2, 3), M = 0; };
+
+// curriculum knobs handed to the kernels (host keeps the python doubles, fetch_env.py:340-348,404-415,561-563)
+struct Ranges {
+    float obj_range, max_obj_range, wrong_obj_range;
+};
+
+// ---------------------------------------------------------------- Philox + elementary functions
+struct U4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ U4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return U4{c0, c1, c2, c3};
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
+__device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-07f; }
+
+__device__ __forceinline__ float bp_log(float x) {
+    uint32_t ix = __float_as_uint(x);
+    ix += 0x3f800000u - 0x3f3504f3u;
+    int e = (int)(ix >> 23) - 127;
+    ix = (ix & 0x007fffffu) + 0x3f3504f3u;
+    float f = __uint_as_float(ix) - 1.0f;
+    float s = f / (2.0f + f);
+    float z = s * s;
+    float w = z * z;
+    float t1 = w * (0.40000972152f + w * 0.24279078841f);
+    float t2 = z * (0.66666662693f + w * 0.28498786688f);
+    float R = t2 + t1;
+    float hfsq = 0.5f * f * f;
+    float dk = (float)e;
+    return ((s * (hfsq + R) + dk * 9.0580006145e-06f) - hfsq + f) + dk * 6.9313812256e-01f;
+}
+
+__device__ __forceinline__ void bp_sincos2pi(float u, float& sn, float& cs) {
+    float t = u * 4.0f;
+    int k = (int)(t + 0.5f);
+    float f = t - (float)k;
+    float x = f * 1.57079637f;
+    float x2 = x * x;
+    float sp = x + x * x2 * (-0.16666667f + x2 * (0.0083333338f + x2 * (-0.00019841270f)));
+    float cp = 1.0f + x2 * (-0.5f + x2 * (0.041666668f + x2 * (-0.0013888889f + x2 * 2.4801588e-05f)));
+    switch (k & 3) {
+        case 0: sn = sp; cs = cp; break;
+        case 1: sn = cp; cs = -sp; break;
+        case 2: sn = -sp; cs = -cp; break;
+        default: sn = -cp; cs = sp; break;
+    }
+}
+
+__device__ __forceinline__ float bp_atan2(float s, float c) {
+    float as = fabsf(s), ac = fabsf(c);
+    float mx = as > ac ? as : ac;
+    float mn = as > ac ? ac : as;
+    if (mx == 0.0f) return 0.0f;
+    float a = mn / mx;
+    float off = 0.0f;
+    if (a > 0.41421357f) {
+        a = (a - 1.0f) / (a + 1.0f);
+        off = 0.78539819f;
+    }
+    float a2 = a * a;
+    float p = 0.076923080f;
+    p = -0.090909094f + a2 * p;
+    p = 0.11111111f + a2 * p;
+    p = -0.14285715f + a2 * p;
+    p = 0.2f + a2 * p;
+    p = -0.33333334f + a2 * p;
+    float r = off + (a + a * a2 * p);
+    if (as > ac) r = 1.57079637f - r;
+    if (c < 0.0f) r = 3.14159274f - r;
+    if (s < 0.0f) r = -r;
+    return r;
+}
+
+__device__ __forceinline__ void bp_normal2(uint32_t w0, uint32_t w1, float& z0, float& z1) {
+    float u1 = u01_open(w0);
+    float u2 = u01(w1);
+    float r = sqrtf(-2.0f * bp_log(u1));
+    float sn, cs;
+    bp_sincos2pi(u2, sn, cs);
+    z0 = r * cs;
+    z1 = r * sn;
+}
+
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// ---------------------------------------------------------------- env state in registers
+template <int NB>
+struct Env {
+    // dynamics slot (replaces MjSim)
+    float g[3], gv[3];
+    float q[2], qv[2];
+    float px[NB], py[NB], pz[NB], c[NB], s[NB], vx[NB], vy[NB], vz[NB], w[NB];
+    // env logic
+    uint32_t touch_now, touch_ever;  // touch matrix as pair masks: 1 <-> now, 0 <-> ever & ~now, -1 <-> ~ever
+    uint32_t contacts;               // contact pairs of the most recent substep
+    int nb;                          // blocks present (num_objs - 2)
+    int t;
+    int succ;
+    uint32_t episode, draws0, draws1;
+    uint32_t key0, key1;             // Philox key = this env's seed
+};
+
+// per-substep scratch
+template <int NB>
+struct Sub {
+    float ox[NB], oy[NB], oz[NB], dth[NB];
+    bool sup[NB];
+    float gox, goy, qo[2], closed[2];
+};
+
+template <int NB>
+__device__ __forceinline__ void sim_init(Env<NB>& e, bool tower) {
+    e.g[0] = kGrip0X; e.g[1] = kGrip0Y; e.g[2] = kGrip0Z;
+    e.gv[0] = e.gv[1] = e.gv[2] = 0.0f;
+    e.q[0] = e.q[1] = 0.0f; e.qv[0] = e.qv[1] = 0.0f;
+    float z = kZRest;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        e.px[i] = 0.0f; e.py[i] = 0.0f;
+        e.pz[i] = (i < e.nb) ? (tower ? z : kZRest) : 0.0f;
+        z = z + kTwoHB;
+        e.c[i] = 1.0f; e.s[i] = 0.0f;
+        e.vx[i] = e.vy[i] = e.vz[i] = 0.0f; e.w[i] = 0.0f;
+    }
+    e.contacts = 0;
+}
+
+__device__ __forceinline__ void rot_apply(float& c, float& s, float dth) {
+    float c2 = c - s * dth;
+    float s2 = s + c * dth;
+    float n = sqrtf(c2 * c2 + s2 * s2);
+    c = c2 / n;
+    s = s2 / n;
+}
+
+struct Rect { float x, y, c, s, hx, hy; };
+struct Sat { float ov[4], proj[4], rtA[4], rtB[4]; };
+
+__device__ __forceinline__ void sat_eval(const Rect& A, const Rect& B, Sat& o) {
+    float cr = A.c * B.c + A.s * B.s;
+    float sr = A.c * B.s - A.s * B.c;
+    float C = fabsf(cr), S = fabsf(sr);
+    float dx = B.x - A.x, dy = B.y - A.y;
+    float RBu = B.hx * C + B.hy * S;
+    float RBv = B.hx * S + B.hy * C;
+    float RAu = A.hx * C + A.hy * S;
+    float RAv = A.hx * S + A.hy * C;
+    o.proj[0] = dx * A.c + dy * A.s;
+    o.proj[1] = dy * A.c - dx * A.s;
+    o.proj[2] = dx * B.c + dy * B.s;
+    o.proj[3] = dy * B.c - dx * B.s;
+    o.ov[0] = (A.hx + RBu) - fabsf(o.proj[0]);
+    o.ov[1] = (A.hy + RBv) - fabsf(o.proj[1]);
+    o.ov[2] = (RAu + B.hx) - fabsf(o.proj[2]);
+    o.ov[3] = (RAv + B.hy) - fabsf(o.proj[3]);
+    o.rtA[0] = A.hy; o.rtB[0] = RBv;
+    o.rtA[1] = A.hx; o.rtB[1] = RBu;
+    o.rtA[2] = RAv;  o.rtB[2] = B.hy;
+    o.rtA[3] = RAu;  o.rtB[3] = B.hx;
+}
+
+// argmin with first-wins ties; returns the value through `mn`
+__device__ __forceinline__ int sat_argmin(const Sat& o, float& mn) {
+    int k = 0;
+    mn = o.ov[0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (o.ov[i] < mn) { mn = o.ov[i]; k = i; }
+    return k;
+}
+
+__device__ __forceinline__ void sat_contact(const Rect& A, const Rect& B, const Sat& o, int k,
+                                            float& nx, float& ny, float& rnA, float& rnB) {
+    // select by k without dynamic register indexing
+    float pk = k == 0 ? o.proj[0] : k == 1 ? o.proj[1] : k == 2 ? o.proj[2] : o.proj[3];
+    float pt = k == 0 ? o.proj[1] : k == 1 ? o.proj[0] : k == 2 ? o.proj[3] : o.proj[2];
+    float ra = k == 0 ? o.rtA[0] : k == 1 ? o.rtA[1] : k == 2 ? o.rtA[2] : o.rtA[3];
+    float rb = k == 0 ? o.rtB[0] : k == 1 ? o.rtB[1] : k == 2 ? o.rtB[2] : o.rtB[3];
+    float ex = k == 0 ? A.c : k == 1 ? -A.s : k == 2 ? B.c : -B.s;
+    float ey = k == 0 ? A.s : k == 1 ? A.c : k == 2 ? B.s : B.c;
+    float sg = pk >= 0.0f ? 1.0f : -1.0f;
+    nx = sg * ex;
+    ny = sg * ey;
+    float lo = -ra;
+    float lo2 = pt - rb;
+    if (lo2 > lo) lo = lo2;
+    float hi = ra;
+    float hi2 = pt + rb;
+    if (hi2 < hi) hi = hi2;
+    float mid = 0.5f * (lo + hi);
+    float chi = (k & 1) ? sg : -sg;
+    rnA = chi * mid;
+    rnB = chi * (mid - pt);
+}
+
+__device__ __forceinline__ bool over_table(float x, float y) {
+    return fabsf(x - kTblX) <= kTblHX && fabsf(y - kTblY) <= kTblHY;
+}
+
+template <int NB>
+__device__ __forceinline__ void collide_finger_block(Env<NB>& e, Sub<NB>& st, const int f, const int bi) {
+    const float sgn = f == 0 ? 1.0f : -1.0f;
+    Rect A{e.g[0], e.g[1] + sgn * (kFY0 + e.q[f]), 1.0f, 0.0f, kFX, kFY};
+    float az = e.g[2] + kFZOff;
+    Rect B{e.px[bi], e.py[bi], e.c[bi], e.s[bi], kHB, kHB};
+    float dz = e.pz[bi] - az;
+    float ovz = (kFZ + kHB) - fabsf(dz);
+    Sat o;
+    sat_eval(A, B, o);
+    float minxy;
+    int k = sat_argmin(o, minxy);
+    float minov = ovz < minxy ? ovz : minxy;
+    if (!(minov > -kMargin)) return;
+    e.contacts |= pair_bit(0, 2) << bi;  // pair (0, bi+2): consecutive pair indices
+    if (!(minov > 0.0f)) return;
+    if (ovz <= minxy) {
+        if (dz >= 0.0f) {
+            e.pz[bi] = az + (kFZ + kHB);
+            st.sup[bi] = true;
+        } else {
+            e.g[2] = (e.pz[bi] + (kFZ + kHB)) - kFZOff;
+            if (e.gv[2] < 0.0f) e.gv[2] = 0.0f;
+        }
+        return;
+    }
+    float delta = minxy;
+    if (k == 1) {
+        bool inner = (f == 0) ? (o.proj[1] < 0.0f) : (o.proj[1] > 0.0f);
+        if (inner) {
+            float yield = delta < st.closed[f] ? delta : st.closed[f];
+            float room = kQMax - e.q[f];
+            if (yield > room) yield = room;
+            if (yield > 0.0f) {
+                e.q[f] = e.q[f] + yield;
+                e.qv[f] = 0.0f;
+                st.closed[f] = st.closed[f] - yield;
+                delta = delta - yield;
+            }
+            if (!(delta > 0.0f)) return;
+        }
+    }
+    float nx, ny, rnA, rnB;
+    sat_contact(A, B, o, k, nx, ny, rnA, rnB);
+    float fdx = e.g[0] - st.gox;
+    float fdy = (e.g[1] - st.goy) + sgn * (e.q[f] - st.qo[f]);
+    float rel = ((e.px[bi] - st.ox[bi]) - fdx) * nx + ((e.py[bi] - st.oy[bi]) - fdy) * ny;
+    float cap = kDepen - rel;
+    float lam = delta < cap ? delta : cap;
+    if (!(lam > 0.0f)) return;
+    float D = 1.0f + kIInv * (rnB * rnB);
+    float l = lam / D;
+    e.px[bi] = e.px[bi] + nx * l;
+    e.py[bi] = e.py[bi] + ny * l;
+    float dth = (kIInv * rnB) * l;
+    if (dth != 0.0f) {
+        rot_apply(e.c[bi], e.s[bi], dth);
+        st.dth[bi] = st.dth[bi] + dth;
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void collide_block_block(Env<NB>& e, Sub<NB>& st, const int i, const int j) {
+    Rect A{e.px[i], e.py[i], e.c[i], e.s[i], kHB, kHB};
+    Rect B{e.px[j], e.py[j], e.c[j], e.s[j], kHB, kHB};
+    float dz = e.pz[j] - e.pz[i];
+    float ovz = kTwoHB - fabsf(dz);
+    Sat o;
+    sat_eval(A, B, o);
+    float minxy;
+    int k = sat_argmin(o, minxy);
+    float minov = ovz < minxy ? ovz : minxy;
+    if (!(minov > -kMargin)) return;
+    e.contacts |= 1u << pair_index(i + 2, j + 2);
+    if (!(minov > 0.0f)) return;
+    int pin = 0;
+    if (ovz <= minxy) {
+        if (dz >= 0.0f) {
+            if (fabsf(o.proj[0]) <= kHB && fabsf(o.proj[1]) <= kHB) {
+                e.pz[j] = e.pz[i] + kTwoHB;
+                st.sup[j] = true;
+                return;
+            }
+            pin = 1;
+        } else {
+            if (fabsf(o.proj[2]) <= kHB && fabsf(o.proj[3]) <= kHB) {
+                e.pz[i] = e.pz[j] + kTwoHB;
+                st.sup[i] = true;
+                return;
+            }
+            pin = 2;
+        }
+    }
+    float nx, ny, rnA, rnB;
+    sat_contact(A, B, o, k, nx, ny, rnA, rnB);
+    float rel = ((e.px[j] - st.ox[j]) - (e.px[i] - st.ox[i])) * nx + ((e.py[j] - st.oy[j]) - (e.py[i] - st.oy[i])) * ny;
+    float cap = kDepen - rel;
+    float lam = minxy < cap ? minxy : cap;
+    if (!(lam > 0.0f)) return;
+    float wA = pin == 1 ? 0.0f : 1.0f;
+    float wB = pin == 2 ? 0.0f : 1.0f;
+    float D = (wA + wB) + kIInv * (wA * (rnA * rnA) + wB * (rnB * rnB));
+    float l = lam / D;
+    float lA = wA * l, lB = wB * l;
+    e.px[i] = e.px[i] - nx * lA;
+    e.py[i] = e.py[i] - ny * lA;
+    e.px[j] = e.px[j] + nx * lB;
+    e.py[j] = e.py[j] + ny * lB;
+    float dthA = -((kIInv * rnA) * lA);
+    float dthB = (kIInv * rnB) * lB;
+    if (dthA != 0.0f) { rot_apply(e.c[i], e.s[i], dthA); st.dth[i] = st.dth[i] + dthA; }
+    if (dthB != 0.0f) { rot_apply(e.c[j], e.s[j], dthB); st.dth[j] = st.dth[j] + dthB; }
+}
+
+// the gripper part of one substep (steps 1-2 of the spec)
+template <int NB, bool BG>
+__device__ __forceinline__ void substep_gripper(Env<NB>& e, Sub<NB>& st, const float m[3], const float ctrl[2]) {
+    st.closed[0] = st.closed[1] = 0.0f;
+    st.gox = e.g[0]; st.goy = e.g[1];
+    st.qo[0] = e.q[0]; st.qo[1] = e.q[1];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float acc = kKW * (m[k] - e.g[k]) - kBW * e.gv[k];
+        e.gv[k] = e.gv[k] + acc * kH;
+        e.g[k] = e.g[k] + e.gv[k] * kH;
+    }
+    if (e.g[2] < kGZMin) {
+        e.g[2] = kGZMin;
+        if (e.gv[2] < 0.0f) e.gv[2] = 0.0f;
+    }
+    if (!BG) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            float q_old = e.q[f];
+            float acc = kKF * (ctrl[f] - e.q[f]) - kBF * e.qv[f];
+            e.qv[f] = e.qv[f] + acc * kH;
+            e.q[f] = e.q[f] + e.qv[f] * kH;
+            if (e.q[f] < 0.0f) { e.q[f] = 0.0f; if (e.qv[f] < 0.0f) e.qv[f] = 0.0f; }
+            if (e.q[f] > kQMax) { e.q[f] = kQMax; if (e.qv[f] > 0.0f) e.qv[f] = 0.0f; }
+            float cl = q_old - e.q[f];
+            st.closed[f] = cl > 0.0f ? cl : 0.0f;
+        }
+    }
+}
+
+// the cube part of one substep (steps 3-5 of the spec)
+template <int NB>
+__device__ __forceinline__ void substep_blocks(Env<NB>& e, Sub<NB>& st) {
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (i < e.nb) {
+            st.ox[i] = e.px[i]; st.oy[i] = e.py[i]; st.oz[i] = e.pz[i];
+            st.dth[i] = 0.0f;
+            st.sup[i] = false;
+            e.vz[i] = e.vz[i] - kGH;
+            e.px[i] = e.px[i] + e.vx[i] * kH;
+            e.py[i] = e.py[i] + e.vy[i] * kH;
+            e.pz[i] = e.pz[i] + e.vz[i] * kH;
+            if (e.w[i] != 0.0f) {
+                float dth = e.w[i] * kH;
+                rot_apply(e.c[i], e.s[i], dth);
+                st.dth[i] = dth;
+            }
+        }
+    }
+    e.contacts = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (i < e.nb) {
+            if (over_table(e.px[i], e.py[i])) {
+                if (e.pz[i] - kZRest < kMargin) e.contacts |= pair_bit(1, 2) << i;
+                if (e.pz[i] < kZRest) { e.pz[i] = kZRest; st.sup[i] = true; }
+            } else if (e.pz[i] < kZFloor) {
+                e.pz[i] = kZFloor;
+                st.sup[i] = true;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (i < e.nb) {
+            collide_finger_block<NB>(e, st, 0, i);
+            collide_finger_block<NB>(e, st, 1, i);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+#pragma unroll
+        for (int j = i + 1; j < NB; ++j)
+            if (j < e.nb) collide_block_block<NB>(e, st, i, j);
+    if (over_table(e.g[0], e.g[1]) && e.g[2] - kGZMin < kMargin) e.contacts |= pair_bit(0, 1);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (i < e.nb) {
+            e.vx[i] = clampf((e.px[i] - st.ox[i]) * kInvH, -kVMax, kVMax);
+            e.vy[i] = clampf((e.py[i] - st.oy[i]) * kInvH, -kVMax, kVMax);
+            e.vz[i] = clampf((e.pz[i] - st.oz[i]) * kInvH, -kVMax, kVMax);
+            e.w[i] = clampf(st.dth[i] * kInvH, -kWMax, kWMax);
+            if (st.sup[i]) {
+                float sp2 = e.vx[i] * e.vx[i] + e.vy[i] * e.vy[i];
+                if (sp2 <= kFr * kFr) {
+                    e.vx[i] = 0.0f; e.vy[i] = 0.0f;
+                } else {
+                    float sp = sqrtf(sp2);
+                    float kf = (sp - kFr) / sp;
+                    e.vx[i] = e.vx[i] * kf;
+                    e.vy[i] = e.vy[i] * kf;
+                }
+                if (fabsf(e.w[i]) <= kFrW) e.w[i] = 0.0f;
+                else e.w[i] = e.w[i] > 0.0f ? e.w[i] - kFrW : e.w[i] + kFrW;
+            }
+        }
+    }
+}
+
+// _set_action (fetch_env.py:170-185, after the clip of robot_env.py:58) + sim.step() (robot_env.py:60)
+template <int NB, bool BG>
+__device__ __forceinline__ void sim_step(Env<NB>& e, const float a[4]) {
+    float m[3], ctrl[2];
+    m[0] = clampf(e.g[0] + a[0] * kPosScale, kWsXLo, kWsXHi);
+    m[1] = clampf(e.g[1] + a[1] * kPosScale, kWsYLo, kWsYHi);
+    m[2] = clampf(e.g[2] + a[2] * kPosScale, kGZMin, kWsZHi);
+    float ga = BG ? 0.0f : a[3];
+    ctrl[0] = clampf(e.q[0] + ga, 0.0f, kCtrlMax);
+    ctrl[1] = clampf(e.q[1] + ga, 0.0f, kCtrlMax);
+#pragma unroll 1
+    for (int sub = 0; sub < kNSub; ++sub) {
+        Sub<NB> st;
+        substep_gripper<NB, BG>(e, st, m, ctrl);
+        substep_blocks<NB>(e, st);
+    }
+}
+
+// ---------------------------------------------------------------- RNG replay
+template <int NB>
+__device__ __forceinline__ U4 env_draw(Env<NB>& e, int stream, uint32_t ep) {
+    uint32_t& d = stream == 0 ? e.draws0 : e.draws1;
+    U4 r = philox4x32(d, ep, (uint32_t)stream, 0u, e.key0, e.key1);
+    d += 1;
+    return r;
+}
+
+__device__ __forceinline__ bool out_of_table(float x, float y) {  // fetch_env.py:30-32
+    return fabsf(x - kTableX) > kTableW || fabsf(y - kTableY) > kTableH;
+}
+__device__ __forceinline__ float norm2(float x, float y) { return sqrtf(x * x + y * y); }
+
+// direction = normal(2)/|.|, mag = uniform(lo, hi) from the global np.random (stream 1)
+template <int NB>
+__device__ __forceinline__ void sample_around(Env<NB>& e, uint32_t ep, float bx, float by, float lo, float hi, float& x, float& y) {
+    U4 r = env_draw(e, 1, ep);
+    float d0, d1;
+    bp_normal2(r.x, r.y, d0, d1);
+    float n = norm2(d0, d1);
+    d0 = d0 / n; d1 = d1 / n;
+    U4 r2 = env_draw(e, 1, ep);
+    float mag = lo + (hi - lo) * u01(r2.x);
+    x = bx + d0 * mag;
+    y = by + d1 * mag;
+}
+
+template <int NB>
+__device__ __forceinline__ void sample_blue(Env<NB>& e, uint32_t ep, float r, float& x, float& y) {  // fetch_env.py:475-480
+    float half = r / 2.0f;
+    int it = 0;
+    do {
+        U4 w = env_draw(e, 0, ep);
+        float lo = -half;
+        x = kGrip0X + (lo + (half - lo) * u01(w.x));
+        y = kGrip0Y + (lo + (half - lo) * u01(w.y));
+    } while (out_of_table(x, y) && ++it < kMaxSpawnAttempts);
+}
+
+// _randomize_objects for every env id; `ep` is the Philox episode counter to draw under
+template <int ID>
+__device__ __forceinline__ void randomize_objects(Env<Cfg<ID>::NB>& e, uint32_t ep, bool test, const Ranges& rg) {
+    constexpr int NB = Cfg<ID>::NB;
+    if (ID == 0 || ID == 2) {  // GripperTouch fetch_env.py:328-336, ToppleTower :777-787
+        float r = rg.obj_range;
+        float x = kGrip0X, y = kGrip0Y;
+        int it = 0;
+        while (norm2(x - kGrip0X, y - kGrip0Y) < 0.1f && it++ < kMaxSpawnAttempts) {
+            U4 w = env_draw(e, 0, ep);
+            float lo = -r;
+            x = kGrip0X + (lo + (r - lo) * u01(w.x));
+            y = kGrip0Y + (lo + (r - lo) * u01(w.y));
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) { e.px[i] = x; e.py[i] = y; }
+    } else if (ID == 1 || ID == 3) {  // BlocksTouch fetch_env.py:370-399
+        float r = test ? rg.max_obj_range : rg.obj_range;
+        float half = r / 2.0f;
+        U4 w = env_draw(e, 0, ep);
+        float lo = -half;
+        float x0 = kGrip0X + (lo + (half - lo) * u01(w.x));
+        float y0 = kGrip0Y + (lo + (half - lo) * u01(w.y));
+        e.px[0] = x0; e.py[0] = y0;
+        float x, y;
+        int it = 0;
+        do {
+            sample_around(e, ep, x0, y0, kMinBlockDist, r, x, y);
+        } while (out_of_table(x, y) && ++it < kMaxSpawnAttempts);
+        if (NB > 1) { e.px[NB > 1 ? 1 : 0] = x; e.py[NB > 1 ? 1 : 0] = y; }
+    } else if (ID == 4 || ID == 5) {  // BlocksTouchChoose fetch_env.py:448-517 (challenge=False)
+        float r, wrong_r;
+        if (test) { r = rg.max_obj_range; wrong_r = 0.0f; }
+        else { r = rg.obj_range; wrong_r = rg.wrong_obj_range; }
+        float max_wrong_r = rg.max_obj_range;
+        float bx, by, gx, gy, wx, wy;
+        sample_blue(e, ep, r, bx, by);
+        int it = 0;
+        do {
+            sample_around(e, ep, bx, by, kMinBlockDist, r, gx, gy);
+        } while (out_of_table(gx, gy) && ++it < kMaxSpawnAttempts);
+        float cx = (bx + gx) / 2.0f, cy = (by + gy) / 2.0f;
+        it = 0;
+        bool again;
+        do {
+            sample_around(e, ep, cx, cy, wrong_r, max_wrong_r, wx, wy);
+            again = out_of_table(wx, wy) || norm2(wx - bx, wy - by) < kMinBlockDist || norm2(wx - gx, wy - gy) < kMinBlockDist;
+        } while (again && ++it < kMaxSpawnAttempts);
+        // colours [GREEN, BLUE, GREY]: green = 0, blue = 1, wrong = 2 (fetch_env.py:465-473)
+        constexpr int iG = 0, iB = NB > 1 ? 1 : 0, iW = NB > 2 ? 2 : 0;
+        e.px[iB] = bx; e.py[iB] = by;
+        e.px[iG] = gx; e.py[iG] = gy;
+        e.px[iW] = wx; e.py[iW] = wy;
+    } else {  // BlocksTouchVariation fetch_env.py:697-764
+        float r = test ? rg.max_obj_range : rg.obj_range;
+        float ppx[4], ppy[4];
+        float bx, by, gx, gy;
+        sample_blue(e, ep, r, bx, by);
+        int it = 0;
+        do {
+            sample_around(e, ep, bx, by, kMinBlockDist, r, gx, gy);
+        } while (out_of_table(gx, gy) && ++it < kMaxSpawnAttempts);
+        constexpr int iG = 0, iB = NB > 1 ? 1 : 0;
+        e.px[iB] = bx; e.py[iB] = by;
+        e.px[iG] = gx; e.py[iG] = gy;
+        ppx[0] = bx; ppy[0] = by; ppx[1] = gx; ppy[1] = gy;
+#pragma unroll
+        for (int i = 2; i < NB; ++i) {
+            if (i < e.nb) {
+                float x, y;
+                bool again;
+                it = 0;
+                do {
+                    U4 wa = env_draw(e, 0, ep);  // _sample_from_table fetch_env.py:88-90
+                    U4 wb = env_draw(e, 0, ep);
+                    float ux = -kTableW + (kTableW - (-kTableW)) * u01(wa.x);
+                    float uy = -kTableH + (kTableH - (-kTableH)) * u01(wb.x);
+                    x = kTableX + ux;
+                    y = kTableY + uy;
+                    bool hit = false;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        if (p < i && !hit && norm2(x - ppx[p], y - ppy[p]) < kMinBlockDist) hit = true;
+                    again = hit ? true : out_of_table(x, y);
+                } while (again && ++it < kMaxSpawnAttempts);
+                e.px[i] = x; e.py[i] = y;
+                ppx[i] = x; ppy[i] = y;
+            }
+        }
+    }
+}
+
+// RobotEnv.reset (robot_env.py:71-82) + _reset_sim (fetch_env.py:247-255, Variation :646-679) + TimeLimit reset
+template <int ID>
+__device__ __forceinline__ void env_reset(Env<Cfg<ID>::NB>& e, const Ranges& rg) {
+    using C = Cfg<ID>;
+    e.draws0 = 0; e.draws1 = 0;
+    uint32_t ep = e.episode;
+    if (C::VAR) {
+        U4 w = env_draw(e, 0, ep);
+        int num_grey = (int)__umulhi(w.x, 3u);  // np_random.randint(3), :647
+        e.nb = 2 + num_grey;
+        e.touch_now = 0; e.touch_ever = 0;      // achieved_goal = -1, :663
+    }
+    sim_init<C::NB>(e, ID == 2);
+    randomize_objects<ID>(e, ep, false, rg);
+    e.succ = 0;
+    e.t = 0;
+    e.episode = ep + 1;
+}
+
+// reward of the env's own touch matrix against its goal: fetch_env.py:135-143 on
+// ag in {-1,0,1}: d = sum(ag*g), c = count_nonzero(g); both symmetric entries counted.
+template <int ID>
+__device__ __forceinline__ float env_reward(uint32_t now, uint32_t ever) {
+    using C = Cfg<ID>;
+    int sp = __popc(now & C::P) - __popc(~ever & C::P);   // sum of ag over the +1 goal pairs
+    int sm = __popc(now & C::M) - __popc(~ever & C::M);   // sum of ag over the -1 goal pairs
+    int d = 2 * (sp - sm);
+    int c = 2 * (__popc(C::P) + __popc(C::M));
+    return (d != c) ? -1.0f : -0.0f;
+}
+
+// value of touch-matrix entry (i, j) as the reference stores it
+__device__ __forceinline__ float ag_value(uint32_t now, uint32_t ever, int i, int j) {
+    if (i == j) return -1.0f;  // never set: no self contacts (fetch_env.py:78)
+    int lo = i < j ? i : j, hi = i < j ? j : i;
+    uint32_t b = 1u << pair_index(lo, hi);
+    return (now & b) ? 1.0f : ((ever & b) ? 0.0f : -1.0f);
+}
+
+// _get_obs (fetch_env.py:187-228; Variation :567-621) into a row of DIMO floats with stride `os`
+template <int ID, typename Store>
+__device__ __forceinline__ void env_write_obs(const Env<Cfg<ID>::NB>& e, Store&& put) {
+    using C = Cfg<ID>;
+    constexpr int NB = C::NB;
+    float gvp0 = e.gv[0] * kDt, gvp1 = e.gv[1] * kDt, gvp2 = e.gv[2] * kDt;
+    int o = 0;
+    if (C::VAR) put(o++, (float)e.nb);
+    put(o++, e.g[0]); put(o++, e.g[1]); put(o++, e.g[2]);
+    put(o++, e.q[0]); put(o++, e.q[1]);
+    put(o++, gvp0); put(o++, gvp1); put(o++, gvp2);
+    put(o++, e.qv[0] * kDt); put(o++, e.qv[1] * kDt);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        constexpr int per = C::VAR ? 19 : 15;
+        const bool live = i < e.nb;
+        put(o + 0, live ? e.px[i] : 0.0f);
+        put(o + 1, live ? e.py[i] : 0.0f);
+        put(o + 2, live ? e.pz[i] : 0.0f);
+        put(o + 3, live ? e.px[i] - e.g[0] : 0.0f);
+        put(o + 4, live ? e.py[i] - e.g[1] : 0.0f);
+        put(o + 5, live ? e.pz[i] - e.g[2] : 0.0f);
+        put(o + 6, 0.0f);
+        put(o + 7, 0.0f);
+        put(o + 8, live ? bp_atan2(e.s[i], e.c[i]) : 0.0f);
+        put(o + 9, live ? e.vx[i] * kDt - gvp0 : 0.0f);
+        put(o + 10, live ? e.vy[i] * kDt - gvp1 : 0.0f);
+        put(o + 11, live ? e.vz[i] * kDt - gvp2 : 0.0f);
+        put(o + 12, 0.0f);
+        put(o + 13, 0.0f);
+        put(o + 14, live ? e.w[i] * kDt : 0.0f);
+        if (C::VAR) {
+            // one_hot_color of [GREEN, BLUE, GREY, GREY] (fetch_env.py:599,632-639): GREY=0, GREEN=2, BLUE=3
+            const int col = i == 0 ? 2 : (i == 1 ? 3 : 0);
+            put(o + 15, live && col == 0 ? 1.0f : 0.0f);
+            put(o + 16, 0.0f);
+            put(o + 17, live && col == 2 ? 1.0f : 0.0f);
+            put(o + 18, live && col == 3 ? 1.0f : 0.0f);
+        }
+        o += per;
+    }
+}
+
+template <int ID, typename Store>
+__device__ __forceinline__ void env_write_ag(uint32_t now, uint32_t ever, Store&& put) {
+    using C = Cfg<ID>;
+    constexpr int N = C::VAR ? kMaxObjs : C::NB + 2;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) put(i * N + j, ag_value(now, ever, i, j));
+}
+
+template <int ID, typename Store>
+__device__ __forceinline__ void env_write_goal(Store&& put) {
+    using C = Cfg<ID>;
+    constexpr int N = C::VAR ? kMaxObjs : C::NB + 2;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            float v = 0.0f;
+            if (i != j) {
+                const int lo = i < j ? i : j, hi = i < j ? j : i;
+                const uint32_t b = 1u << pair_index(lo, hi);
+                v = (C::P & b) ? 1.0f : ((C::M & b) ? -1.0f : 0.0f);
+            }
+            put(i * N + j, v);
+        }
+}
+
+// RobotEnv.step (robot_env.py:57-69) for one env; returns the reward, updates latch and t.
+template <int ID>
+__device__ __forceinline__ float env_step(Env<Cfg<ID>::NB>& e, float a0, float a1, float a2, float a3, int& invalid) {
+    using C = Cfg<ID>;
+    float a[4] = {a0, a1, a2, a3};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float x = a[k];
+        if (!(x == x)) { x = 0.0f; invalid += 1; }
+        a[k] = x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x);  // np.clip, robot_env.py:58
+    }
+    sim_step<C::NB, C::BG>(e, a);
+    // _step_callback fetch_env.py:148-167: 1 -> 0 downgrade, then contacts -> 1
+    e.touch_now = e.contacts;
+    e.touch_ever |= e.contacts;
+    float r = env_reward<ID>(e.touch_now, e.touch_ever);
+    if (r == 0.0f) e.succ = 1;  // _is_success latch, fetch_env.py:275-281
+    e.t += 1;
+    return r;
+}
+
+}  // namespace bp

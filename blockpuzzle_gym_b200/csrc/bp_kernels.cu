@@ -1,0 +1,709 @@
+// bp_kernels.cu -- CUDA kernels (sm_100a) + the C-ABI of include/blockpuzzle_b200.h.
+//
+// Device state layout: field-major SoA, state[f * B + e] (32-bit words), so that
+// a warp of 32 consecutive envs reads/writes every field with one coalesced
+// 128-byte transaction.  Fields: see load_env/store_env.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/blockpuzzle_b200.h"
+#include "bp_device.cuh"
+
+namespace bp {
+
+// ---------------------------------------------------------------- state <-> registers
+template <int NB> __host__ __device__ constexpr int num_fields() { return 17 + 9 * NB; }
+
+template <int NB>
+__device__ __forceinline__ void load_env(const uint32_t* __restrict__ st, int64_t B, int64_t i, Env<NB>& e) {
+    const uint32_t* p = st + i;
+    int f = 0;
+    auto ldf = [&]() { float v = __uint_as_float(p[(int64_t)f * B]); ++f; return v; };
+    auto ldu = [&]() { uint32_t v = p[(int64_t)f * B]; ++f; return v; };
+    e.g[0] = ldf(); e.g[1] = ldf(); e.g[2] = ldf();
+    e.gv[0] = ldf(); e.gv[1] = ldf(); e.gv[2] = ldf();
+    e.q[0] = ldf(); e.q[1] = ldf(); e.qv[0] = ldf(); e.qv[1] = ldf();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        e.px[b] = ldf(); e.py[b] = ldf(); e.pz[b] = ldf();
+        e.c[b] = ldf(); e.s[b] = ldf();
+        e.vx[b] = ldf(); e.vy[b] = ldf(); e.vz[b] = ldf(); e.w[b] = ldf();
+    }
+    uint32_t touch = ldu();
+    e.touch_now = touch & 0xffffu; e.touch_ever = touch >> 16;
+    uint32_t flags = ldu();
+    e.t = (int)(flags & 0xffu); e.succ = (int)((flags >> 8) & 1u); e.nb = (int)((flags >> 9) & 7u);
+    e.episode = ldu(); e.draws0 = ldu(); e.draws1 = ldu();
+    e.key0 = ldu(); e.key1 = ldu();
+    e.contacts = 0;
+}
+
+template <int NB>
+__device__ __forceinline__ void store_env(uint32_t* __restrict__ st, int64_t B, int64_t i, const Env<NB>& e) {
+    uint32_t* p = st + i;
+    int f = 0;
+    auto stf = [&](float v) { p[(int64_t)f * B] = __float_as_uint(v); ++f; };
+    auto stu = [&](uint32_t v) { p[(int64_t)f * B] = v; ++f; };
+    stf(e.g[0]); stf(e.g[1]); stf(e.g[2]);
+    stf(e.gv[0]); stf(e.gv[1]); stf(e.gv[2]);
+    stf(e.q[0]); stf(e.q[1]); stf(e.qv[0]); stf(e.qv[1]);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        stf(e.px[b]); stf(e.py[b]); stf(e.pz[b]);
+        stf(e.c[b]); stf(e.s[b]);
+        stf(e.vx[b]); stf(e.vy[b]); stf(e.vz[b]); stf(e.w[b]);
+    }
+    stu(e.touch_now | (e.touch_ever << 16));
+    stu((uint32_t)e.t | ((uint32_t)e.succ << 8) | ((uint32_t)e.nb << 9));
+    stu(e.episode); stu(e.draws0); stu(e.draws1);
+    stu(e.key0); stu(e.key1);
+}
+
+// ---------------------------------------------------------------- kernels
+// construction: what BlocksEnv.__init__ leaves (fetch_env.py:75-86, robot_env.py:33-37)
+template <int ID>
+__global__ void init_kernel(uint32_t* st, int64_t B) {
+    using C = Cfg<ID>;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Env<C::NB> e;
+    e.nb = C::NB;
+    sim_init<C::NB>(e, ID == 2);
+    e.touch_now = 0; e.touch_ever = 0;  // achieved_goal = -1 everywhere, fetch_env.py:78
+    e.t = 0; e.succ = 0; e.episode = 0; e.draws0 = 0; e.draws1 = 0; e.key0 = 0; e.key1 = 0;
+    store_env<C::NB>(st, B, i, e);
+}
+
+// RolloutStudent.seed: env idx gets seed + 1000*idx (rollout.py:206-210)
+__global__ void seed_kernel(uint32_t* st, int64_t B, int nf, uint64_t seed, uint64_t env_offset) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    uint64_t s = seed + 1000ull * (env_offset + (uint64_t)i);
+    st[(int64_t)(nf - 5) * B + i] = 0;  // episode
+    st[(int64_t)(nf - 4) * B + i] = 0;  // draws0
+    st[(int64_t)(nf - 3) * B + i] = 0;  // draws1
+    st[(int64_t)(nf - 2) * B + i] = (uint32_t)s;
+    st[(int64_t)(nf - 1) * B + i] = (uint32_t)(s >> 32);
+}
+
+template <int ID>
+__device__ __forceinline__ void write_row_obs(const Env<Cfg<ID>::NB>& e, float* row) {
+    env_write_obs<ID>(e, [&](int k, float v) { row[k] = v; });
+}
+template <int ID>
+__device__ __forceinline__ void write_row_ag(const Env<Cfg<ID>::NB>& e, float* row) {
+    env_write_ag<ID>(e.touch_now, e.touch_ever, [&](int k, float v) { row[k] = v; });
+}
+template <int ID>
+__device__ __forceinline__ void write_row_goal(float* row) {
+    env_write_goal<ID>([&](int k, float v) { row[k] = v; });
+}
+
+template <int ID>
+__global__ void reset_kernel(uint32_t* st, int64_t B, const uint8_t* mask, Ranges rg, float* obs, float* ag, float* g) {
+    using C = Cfg<ID>;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    if (mask && !mask[i]) return;
+    Env<C::NB> e;
+    load_env<C::NB>(st, B, i, e);
+    env_reset<ID>(e, rg);
+    store_env<C::NB>(st, B, i, e);
+    if (obs) write_row_obs<ID>(e, obs + i * C::DIMO);
+    if (ag) write_row_ag<ID>(e, ag + i * C::DIMG);
+    if (g) write_row_goal<ID>(g + i * C::DIMG);
+}
+
+// set_test: fetch_env.py:365-368, 443-446 (stale obs, appendix A4); Variation :641-644
+template <int ID>
+__global__ void set_test_kernel(uint32_t* st, int64_t B, Ranges rg, float* obs, float* ag, float* g) {
+    using C = Cfg<ID>;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Env<C::NB> e;
+    load_env<C::NB>(st, B, i, e);
+    if (obs) write_row_obs<ID>(e, obs + i * C::DIMO);
+    if (ag) write_row_ag<ID>(e, ag + i * C::DIMG);
+    if (g) write_row_goal<ID>(g + i * C::DIMG);
+    if (!C::VAR) {
+        randomize_objects<ID>(e, e.episode - 1u, true, rg);
+        store_env<C::NB>(st, B, i, e);
+    }
+}
+
+struct StepArgs {
+    const float* actions;  // [K][B][4] or null
+    float* obs;            // [K][B][DIMO]
+    float* ag;             // [K][B][DIMG]
+    float* reward;         // [K][B]
+    float* success;        // [K][B]
+    uint8_t* done;         // [K][B]
+    float* reset_obs;      // [B][DIMO]
+    float* reset_ag;       // [B][DIMG]
+    float* actions_out;    // [K][B][4]
+    double* stats;
+    int64_t B;             // envs in this launch
+    int64_t stateB;        // stride of the state arrays (envs in the handle)
+    int64_t env0;          // first env of this launch inside the handle
+    int K;
+    int auto_reset;
+    Ranges rg;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// v0: one thread per env, K fused steps, state in registers, direct stores.
+template <int ID>
+__global__ void __launch_bounds__(128) step_kernel_simple(uint32_t* st, StepArgs p) {
+    using C = Cfg<ID>;
+    int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index inside this launch
+    const bool live = li < p.B;
+    float n_ep = 0.f, n_su = 0.f, n_st = 0.f, n_inv = 0.f, r_sum = 0.f;
+    if (live) {
+        const int64_t i = p.env0 + li;
+        Env<C::NB> e;
+        load_env<C::NB>(st, p.stateB, i, e);
+        for (int k = 0; k < p.K; ++k) {
+            const int64_t row = (int64_t)k * p.B + li;
+            float4 a;
+            if (p.actions) {
+                a = reinterpret_cast<const float4*>(p.actions)[row];
+            } else {
+                U4 w = philox4x32((uint32_t)e.t, e.episode - 1u, 2u, 0u, e.key0, e.key1);
+                a = make_float4(2.0f * u01(w.x) - 1.0f, 2.0f * u01(w.y) - 1.0f, 2.0f * u01(w.z) - 1.0f, 2.0f * u01(w.w) - 1.0f);
+            }
+            if (p.actions_out) reinterpret_cast<float4*>(p.actions_out)[row] = a;
+            int inv = 0;
+            float r = env_step<ID>(e, a.x, a.y, a.z, a.w, inv);
+            if (p.obs) write_row_obs<ID>(e, p.obs + row * C::DIMO);
+            if (p.ag) write_row_ag<ID>(e, p.ag + row * C::DIMG);
+            if (p.reward) p.reward[row] = r;
+            if (p.success) p.success[row] = (float)e.succ;
+            const bool done = e.t >= kT;
+            if (p.done) p.done[row] = done ? 1 : 0;
+            n_st += 1.f; n_inv += (float)inv; r_sum += r;
+            if (done) {
+                n_ep += 1.f; n_su += (float)e.succ;
+                if (p.auto_reset) {
+                    env_reset<ID>(e, p.rg);
+                    if (p.reset_obs) write_row_obs<ID>(e, p.reset_obs + li * C::DIMO);
+                    if (p.reset_ag) write_row_ag<ID>(e, p.reset_ag + li * C::DIMG);
+                }
+            }
+        }
+        store_env<C::NB>(st, p.stateB, i, e);
+    }
+    n_ep = warp_sum(n_ep); n_su = warp_sum(n_su); n_st = warp_sum(n_st); n_inv = warp_sum(n_inv); r_sum = warp_sum(r_sum);
+    if ((threadIdx.x & 31) == 0 && p.stats) {
+        if (n_ep != 0.f) atomicAdd(p.stats + BP_STAT_EPISODES, (double)n_ep);
+        if (n_su != 0.f) atomicAdd(p.stats + BP_STAT_SUCCESSES, (double)n_su);
+        if (n_st != 0.f) atomicAdd(p.stats + BP_STAT_STEPS, (double)n_st);
+        if (n_inv != 0.f) atomicAdd(p.stats + BP_STAT_INVALID, (double)n_inv);
+        if (r_sum != 0.f) atomicAdd(p.stats + BP_STAT_REWARD_SUM, (double)r_sum);
+    }
+}
+
+template <int ID>
+__global__ void get_state_kernel(const uint32_t* st, int64_t B, bp_env_state* out) {
+    using C = Cfg<ID>;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Env<C::NB> e;
+    load_env<C::NB>(st, B, i, e);
+    bp_env_state s;
+    memset(&s, 0, sizeof(s));
+    for (int k = 0; k < 3; ++k) { s.grip_pos[k] = e.g[k]; s.grip_vel[k] = e.gv[k]; }
+    for (int k = 0; k < 2; ++k) { s.finger_q[k] = e.q[k]; s.finger_qv[k] = e.qv[k]; }
+#pragma unroll
+    for (int b = 0; b < C::NB; ++b) {
+        if (b < e.nb) {
+            s.blk_pos[b][0] = e.px[b]; s.blk_pos[b][1] = e.py[b]; s.blk_pos[b][2] = e.pz[b];
+            s.blk_cs[b][0] = e.c[b]; s.blk_cs[b][1] = e.s[b];
+            s.blk_vel[b][0] = e.vx[b]; s.blk_vel[b][1] = e.vy[b]; s.blk_vel[b][2] = e.vz[b];
+            s.blk_w[b] = e.w[b];
+        }
+    }
+    constexpr int N = C::VAR ? kMaxObjs : C::NB + 2;
+    for (int k = 0; k < BP_MAX_DIMG; ++k) s.ag[k] = -1;  // rows beyond N*N keep the constructor's -1
+    for (int a = 0; a < N; ++a)
+        for (int b = 0; b < N; ++b) s.ag[a * N + b] = (int8_t)ag_value(e.touch_now, e.touch_ever, a, b);
+    s.num_objs = e.nb + 2;
+    s.has_succeeded = e.succ;
+    s.t = e.t;
+    s.episode = e.episode;
+    s.draws[0] = e.draws0; s.draws[1] = e.draws1;
+    out[i] = s;
+}
+
+template <int ID>
+__global__ void set_state_kernel(uint32_t* st, int64_t B, const bp_env_state* in) {
+    using C = Cfg<ID>;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    Env<C::NB> e;
+    load_env<C::NB>(st, B, i, e);  // keeps the Philox key
+    const bp_env_state& s = in[i];
+    for (int k = 0; k < 3; ++k) { e.g[k] = s.grip_pos[k]; e.gv[k] = s.grip_vel[k]; }
+    for (int k = 0; k < 2; ++k) { e.q[k] = s.finger_q[k]; e.qv[k] = s.finger_qv[k]; }
+#pragma unroll
+    for (int b = 0; b < C::NB; ++b) {
+        e.px[b] = s.blk_pos[b][0]; e.py[b] = s.blk_pos[b][1]; e.pz[b] = s.blk_pos[b][2];
+        e.c[b] = s.blk_cs[b][0]; e.s[b] = s.blk_cs[b][1];
+        e.vx[b] = s.blk_vel[b][0]; e.vy[b] = s.blk_vel[b][1]; e.vz[b] = s.blk_vel[b][2];
+        e.w[b] = s.blk_w[b];
+    }
+    constexpr int N = C::VAR ? kMaxObjs : C::NB + 2;
+    e.touch_now = 0; e.touch_ever = 0;
+    for (int a = 0; a < N; ++a)
+        for (int b = a + 1; b < N; ++b) {
+            int v = s.ag[a * N + b];
+            uint32_t bit = 1u << pair_index(a, b);
+            if (v == 1) { e.touch_now |= bit; e.touch_ever |= bit; }
+            else if (v == 0) e.touch_ever |= bit;
+        }
+    e.nb = s.num_objs - 2;
+    e.succ = s.has_succeeded;
+    e.t = s.t;
+    e.episode = s.episode;
+    e.draws0 = s.draws[0]; e.draws1 = s.draws[1];
+    store_env<C::NB>(st, B, i, e);
+}
+
+// BlocksEnv.compute_reward (fetch_env.py:135-143): one thread per row, 128-bit loads when dimg % 4 == 0
+__global__ void compute_reward_kernel(const float* __restrict__ ag, const float* __restrict__ g, int64_t n, int dimg, float* __restrict__ r) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = ag + i * dimg;
+    const float* b = g + i * dimg;
+    float d = 0.0f;
+    int c = 0;
+    if ((dimg & 3) == 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        for (int k = 0; k < dimg / 4; ++k) {
+            float4 x = __ldg(a4 + k), y = __ldg(b4 + k);
+            d = d + x.x * y.x; d = d + x.y * y.y; d = d + x.z * y.z; d = d + x.w * y.w;
+            c += (y.x != 0.0f) + (y.y != 0.0f) + (y.z != 0.0f) + (y.w != 0.0f);
+        }
+    } else {
+        for (int k = 0; k < dimg; ++k) {
+            float x = __ldg(a + k), y = __ldg(b + k);
+            d = d + x * y;
+            c += (y != 0.0f);
+        }
+    }
+    r[i] = (d != (float)c) ? -1.0f : -0.0f;
+}
+
+// HER relabel + reward (baselines.her.her._sample_her_transitions [upstream]; config.py:107-123)
+__global__ void her_relabel_kernel(const float* __restrict__ ep_ag, const float* __restrict__ ep_g, int B, int T, int dimg,
+                                   int64_t n, float future_p, uint32_t k0, uint32_t k1, int64_t index_offset,
+                                   int32_t* ep_idx, int32_t* t_idx, int32_t* fut_t, float* ag2_out, float* g_out, float* r_out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t gi = (uint64_t)(i + index_offset);
+    U4 w = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 3u, 0u, k0, k1);
+    int e = (int)__umulhi(w.x, (uint32_t)B);
+    int t = (int)__umulhi(w.y, (uint32_t)T);
+    bool her = u01(w.z) < future_p;
+    int off = (int)(u01(w.w) * (float)(T - t));
+    int ft = t + 1 + off;
+    const float* ag2 = ep_ag + ((int64_t)e * (T + 1) + (t + 1)) * dimg;
+    const float* gs = her ? ep_ag + ((int64_t)e * (T + 1) + ft) * dimg : ep_g + ((int64_t)e * T + t) * dimg;
+    float d = 0.0f;
+    int c = 0;
+    if ((dimg & 3) == 0) {
+        for (int k = 0; k < dimg / 4; ++k) {
+            float4 x = __ldg(reinterpret_cast<const float4*>(ag2) + k);
+            float4 y = __ldg(reinterpret_cast<const float4*>(gs) + k);
+            d = d + x.x * y.x; d = d + x.y * y.y; d = d + x.z * y.z; d = d + x.w * y.w;
+            c += (y.x != 0.0f) + (y.y != 0.0f) + (y.z != 0.0f) + (y.w != 0.0f);
+            if (g_out) reinterpret_cast<float4*>(g_out + i * dimg)[k] = y;
+            if (ag2_out) reinterpret_cast<float4*>(ag2_out + i * dimg)[k] = x;
+        }
+    } else {
+        for (int k = 0; k < dimg; ++k) {
+            float x = __ldg(ag2 + k), y = __ldg(gs + k);
+            d = d + x * y;
+            c += (y != 0.0f);
+            if (g_out) g_out[i * dimg + k] = y;
+            if (ag2_out) ag2_out[i * dimg + k] = x;
+        }
+    }
+    if (r_out) r_out[i] = (d != (float)c) ? -1.0f : -0.0f;
+    if (ep_idx) ep_idx[i] = e;
+    if (t_idx) t_idx[i] = t;
+    if (fut_t) fut_t[i] = her ? ft : -1;
+}
+
+}  // namespace bp
+
+// ======================================================================= C-ABI
+using namespace bp;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(BP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));      \
+    } while (0)
+
+static const char* kNames[BP_NUM_ENV_IDS] = {
+    "GripperTouch-v0", "BlocksTouch-v0", "ToppleTower-v0", "BlocksTouchCurriculum-v0",
+    "BlocksTouchChoose-v0", "BlocksTouchChooseCurriculum-v0", "BlocksTouchVariation-v0"};
+static const int kNB[BP_NUM_ENV_IDS] = {1, 2, 4, 2, 3, 3, 4};
+static const int kDimO[BP_NUM_ENV_IDS] = {25, 40, 70, 40, 55, 55, 87};
+static const int kDimG[BP_NUM_ENV_IDS] = {9, 16, 36, 16, 25, 25, 36};
+
+struct bp_handle {
+    int env_id = 0;
+    int device = 0;
+    int64_t B = 0;
+    uint64_t env_offset = 0;
+    int nf = 0;
+    uint32_t* d_state = nullptr;
+    double* d_stats = nullptr;
+    // curriculum knobs: python floats of fetch_env.py:340-348, 404-415, 561-563
+    double obj_range = 0.15, obj_range_step = 0, max_obj_range = 0.15;
+    double wrong_obj_range = 0, wrong_obj_range_step = 0;
+    bool has_step = false, has_curriculum = false;
+    int difficulty = 0;
+    // bp_step_host staging
+    cudaStream_t hs[2] = {nullptr, nullptr};
+    float* d_stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+};
+
+static Ranges ranges_of(const bp_handle* h) {
+    return Ranges{(float)h->obj_range, (float)h->max_obj_range, (float)h->wrong_obj_range};
+}
+
+template <typename F>
+static int dispatch(int env_id, F&& f) {
+    switch (env_id) {
+        case 0: return f(std::integral_constant<int, 0>());
+        case 1: return f(std::integral_constant<int, 1>());
+        case 2: return f(std::integral_constant<int, 2>());
+        case 3: return f(std::integral_constant<int, 3>());
+        case 4: return f(std::integral_constant<int, 4>());
+        case 5: return f(std::integral_constant<int, 5>());
+        case 6: return f(std::integral_constant<int, 6>());
+        default: return fail(BP_ERR_INVALID_ARG, "unknown env id");
+    }
+}
+
+static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+extern "C" {
+
+int bp_abi_version(void) { return BP_ABI_VERSION; }
+const char* bp_last_error(void) { return g_err.c_str(); }
+
+int bp_env_dims(int env_id, int* dimo, int* dimg, int* nblocks) {
+    if (env_id < 0 || env_id >= BP_NUM_ENV_IDS) return fail(BP_ERR_INVALID_ARG, "unknown env id");
+    if (dimo) *dimo = kDimO[env_id];
+    if (dimg) *dimg = kDimG[env_id];
+    if (nblocks) *nblocks = kNB[env_id];
+    return BP_OK;
+}
+
+int bp_env_id_from_name(const char* name) {
+    if (!name) return fail(BP_ERR_INVALID_ARG, "null name");
+    for (int i = 0; i < BP_NUM_ENV_IDS; ++i)
+        if (strcmp(name, kNames[i]) == 0) return i;
+    return fail(BP_ERR_INVALID_ARG, std::string("no registered env id ") + name);
+}
+
+const char* bp_env_name(int env_id) {
+    if (env_id < 0 || env_id >= BP_NUM_ENV_IDS) return nullptr;
+    return kNames[env_id];
+}
+
+int bp_create(int env_id, int64_t num_envs, int device, uint64_t env_index_offset, bp_handle** out) {
+    if (!out) return fail(BP_ERR_INVALID_ARG, "out is null");
+    if (env_id < 0 || env_id >= BP_NUM_ENV_IDS) return fail(BP_ERR_INVALID_ARG, "unknown env id");
+    if (num_envs <= 0) return fail(BP_ERR_INVALID_ARG, "num_envs must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(BP_ERR_NO_DEVICE, "no CUDA device: blockpuzzle_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(BP_ERR_INVALID_ARG, "bad device index");
+    CU(cudaSetDevice(device));
+    bp_handle* h = new bp_handle();
+    h->env_id = env_id; h->device = device; h->B = num_envs; h->env_offset = env_index_offset;
+    h->nf = 17 + 9 * kNB[env_id];
+    switch (env_id) {  // fetch_env.py:340-348, 404-415, 561-563 on top of tasks.py obj_range=0.15
+        case BP_BLOCKS_TOUCH: h->max_obj_range = h->obj_range; h->obj_range_step = 0; h->has_step = true; h->has_curriculum = true; break;
+        case BP_BLOCKS_TOUCH_CURRICULUM:
+        case BP_BLOCKS_TOUCH_VARIATION:
+            h->obj_range = 0.08; h->obj_range_step = 0.025; h->max_obj_range = 0.2; h->has_step = true; h->has_curriculum = true; break;
+        case BP_BLOCKS_TOUCH_CHOOSE: h->wrong_obj_range = 0; h->max_obj_range = 0.2; h->has_step = false; h->has_curriculum = true; break;
+        case BP_BLOCKS_TOUCH_CHOOSE_CURRICULUM:
+            h->obj_range = 0.08; h->obj_range_step = 0.025; h->wrong_obj_range = 0.2; h->wrong_obj_range_step = 0.02;
+            h->max_obj_range = 0.3; h->has_step = true; h->has_curriculum = true; break;
+        default: break;
+    }
+    cudaError_t e1 = cudaMalloc(&h->d_state, sizeof(uint32_t) * (size_t)h->nf * (size_t)num_envs);
+    cudaError_t e2 = cudaMalloc(&h->d_stats, sizeof(double) * BP_NUM_STATS);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+        cudaFree(h->d_state); cudaFree(h->d_stats); delete h;
+        return fail(BP_ERR_CUDA, "cudaMalloc of env state failed");
+    }
+    cudaMemset(h->d_stats, 0, sizeof(double) * BP_NUM_STATS);
+    int rc = dispatch(env_id, [&](auto id) {
+        init_kernel<decltype(id)::value><<<nblk(num_envs, 128), 128>>>(h->d_state, num_envs);
+        return BP_OK;
+    });
+    if (rc != BP_OK) { bp_destroy(h); return rc; }
+    seed_kernel<<<nblk(num_envs, 128), 128>>>(h->d_state, num_envs, h->nf, 0, env_index_offset);
+    cudaError_t e3 = cudaDeviceSynchronize();
+    if (e3 != cudaSuccess) { bp_destroy(h); return fail(BP_ERR_CUDA, std::string("init: ") + cudaGetErrorString(e3)); }
+    *out = h;
+    return BP_OK;
+}
+
+int bp_destroy(bp_handle* h) {
+    if (!h) return BP_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_state);
+    cudaFree(h->d_stats);
+    for (int i = 0; i < 2; ++i) {
+        if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+        if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
+    }
+    delete h;
+    return BP_OK;
+}
+
+int64_t bp_num_envs(const bp_handle* h) { return h ? h->B : 0; }
+
+int bp_seed(bp_handle* h, uint64_t seed, void* stream) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    seed_kernel<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, h->nf, seed, h->env_offset);
+    CU(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_reset(bp_handle* h, const uint8_t* d_mask, float* d_obs, float* d_ag, float* d_g, void* stream) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    Ranges rg = ranges_of(h);
+    int rc = dispatch(h->env_id, [&](auto id) {
+        reset_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, d_mask, rg, d_obs, d_ag, d_g);
+        return BP_OK;
+    });
+    if (rc != BP_OK) return rc;
+    CU(cudaGetLastError());
+    return BP_OK;
+}
+
+static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
+    int rc = dispatch(h->env_id, [&](auto id) {
+        step_kernel_simple<decltype(id)::value><<<nblk(a.B, 128), 128, 0, s>>>(h->d_state, a);
+        return BP_OK;
+    });
+    if (rc != BP_OK) return rc;
+    CU(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_step(bp_handle* h, const float* d_actions, int K, float* d_obs, float* d_ag, float* d_reward,
+            float* d_success, uint8_t* d_done, int auto_reset, float* d_reset_obs, float* d_reset_ag,
+            float* d_actions_out, void* stream) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    if (K <= 0) return fail(BP_ERR_INVALID_ARG, "K must be positive");
+    CU(cudaSetDevice(h->device));
+    StepArgs a{};
+    a.actions = d_actions; a.obs = d_obs; a.ag = d_ag; a.reward = d_reward; a.success = d_success; a.done = d_done;
+    a.reset_obs = d_reset_obs; a.reset_ag = d_reset_ag; a.actions_out = d_actions_out; a.stats = h->d_stats;
+    a.B = h->B; a.stateB = h->B; a.env0 = 0; a.K = K; a.auto_reset = auto_reset; a.rg = ranges_of(h);
+    return launch_step(h, a, (cudaStream_t)stream);
+}
+
+int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, float* h_ag, float* h_reward,
+                 float* h_success, int auto_reset) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    if (K <= 0 || !h_actions) return fail(BP_ERR_INVALID_ARG, "bp_step_host needs actions and K > 0");
+    CU(cudaSetDevice(h->device));
+    const int dimo = kDimO[h->env_id], dimg = kDimG[h->env_id];
+    // chunk of envs: per env and step 4 (action) + dimo + dimg + 2 floats
+    const size_t per_env = (size_t)K * (size_t)(4 + dimo + dimg + 2) * sizeof(float);
+    int64_t chunk = (int64_t)((size_t)(192u << 20) / per_env);
+    if (chunk > h->B) chunk = h->B;
+    chunk &= ~(int64_t)127;
+    if (chunk < 128) chunk = h->B < 128 ? h->B : 128;
+    const size_t need = per_env * (size_t)chunk;
+    if (h->stage_bytes < need) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->d_stage[i]) cudaFree(h->d_stage[i]);
+            h->d_stage[i] = nullptr;
+            CU(cudaMalloc(&h->d_stage[i], need));
+            if (!h->hs[i]) CU(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
+        }
+        h->stage_bytes = need;
+    }
+    // the host arrays are [K][B][dim]; a chunk [K][n][dim] is strided -> 2-D copies
+    int buf = 0;
+    for (int64_t e0 = 0; e0 < h->B; e0 += chunk, buf ^= 1) {
+        const int64_t n = (h->B - e0) < chunk ? (h->B - e0) : chunk;
+        cudaStream_t s = h->hs[buf];
+        float* base = h->d_stage[buf];
+        float* d_act = base;
+        float* d_obs = d_act + (size_t)K * n * 4;
+        float* d_ag = d_obs + (size_t)K * n * dimo;
+        float* d_r = d_ag + (size_t)K * n * dimg;
+        float* d_s = d_r + (size_t)K * n;
+        CU(cudaMemcpy2DAsync(d_act, (size_t)n * 4 * 4, h_actions + e0 * 4, (size_t)h->B * 4 * 4, (size_t)n * 4 * 4, K, cudaMemcpyHostToDevice, s));
+        StepArgs a{};
+        a.actions = d_act; a.obs = h_obs ? d_obs : nullptr; a.ag = h_ag ? d_ag : nullptr;
+        a.reward = h_reward ? d_r : nullptr; a.success = h_success ? d_s : nullptr;
+        a.stats = h->d_stats; a.B = n; a.stateB = h->B; a.env0 = e0; a.K = K; a.auto_reset = auto_reset; a.rg = ranges_of(h);
+        int rc = launch_step(h, a, s);
+        if (rc != BP_OK) return rc;
+        if (h_obs) CU(cudaMemcpy2DAsync(h_obs + e0 * dimo, (size_t)h->B * dimo * 4, d_obs, (size_t)n * dimo * 4, (size_t)n * dimo * 4, K, cudaMemcpyDeviceToHost, s));
+        if (h_ag) CU(cudaMemcpy2DAsync(h_ag + e0 * dimg, (size_t)h->B * dimg * 4, d_ag, (size_t)n * dimg * 4, (size_t)n * dimg * 4, K, cudaMemcpyDeviceToHost, s));
+        if (h_reward) CU(cudaMemcpy2DAsync(h_reward + e0, (size_t)h->B * 4, d_r, (size_t)n * 4, (size_t)n * 4, K, cudaMemcpyDeviceToHost, s));
+        if (h_success) CU(cudaMemcpy2DAsync(h_success + e0, (size_t)h->B * 4, d_s, (size_t)n * 4, (size_t)n * 4, K, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(h->hs[0]));
+    CU(cudaStreamSynchronize(h->hs[1]));
+    return BP_OK;
+}
+
+int bp_set_test(bp_handle* h, float* d_obs, float* d_ag, float* d_g, void* stream) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    if (h->env_id == BP_GRIPPER_TOUCH || h->env_id == BP_TOPPLE_TOWER)
+        return fail(BP_ERR_NOT_IMPLEMENTED, "set_test raises NotImplementedError for this env (fetch_env.py:100-101)");
+    CU(cudaSetDevice(h->device));
+    Ranges rg = ranges_of(h);
+    int rc = dispatch(h->env_id, [&](auto id) {
+        set_test_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, rg, d_obs, d_ag, d_g);
+        return BP_OK;
+    });
+    if (rc != BP_OK) return rc;
+    CU(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_increase_difficulty(bp_handle* h, int* max_reached) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    int ret = 0;
+    switch (h->env_id) {
+        case BP_BLOCKS_TOUCH:
+        case BP_BLOCKS_TOUCH_CURRICULUM:
+        case BP_BLOCKS_TOUCH_VARIATION:  // fetch_env.py:351-358, 623-630
+            h->obj_range += h->obj_range_step;
+            if (h->obj_range > h->max_obj_range) { h->obj_range = h->max_obj_range; ret = 1; }
+            else h->difficulty += 1;
+            break;
+        case BP_BLOCKS_TOUCH_CHOOSE:
+        case BP_BLOCKS_TOUCH_CHOOSE_CURRICULUM:  // fetch_env.py:419-432
+            if (!h->has_step) return fail(BP_ERR_NOT_IMPLEMENTED, "AttributeError: no obj_range_step (fetch_env.py:413-415,420)");
+            h->obj_range += h->obj_range_step;
+            h->wrong_obj_range -= h->wrong_obj_range_step;
+            if (h->obj_range > h->max_obj_range) {
+                h->obj_range = h->max_obj_range;
+                if (h->wrong_obj_range < 0) { h->wrong_obj_range = 0; ret = 1; break; }
+            } else if (h->wrong_obj_range < 0) {
+                h->wrong_obj_range = 0;
+            }
+            h->difficulty += 1;
+            break;
+        default:
+            return fail(BP_ERR_NOT_IMPLEMENTED, "increase_difficulty raises NotImplementedError (fetch_env.py:93-94)");
+    }
+    if (max_reached) *max_reached = ret;
+    return BP_OK;
+}
+
+int bp_get_difficulty(const bp_handle* h, int* difficulty) {
+    if (!h || !difficulty) return fail(BP_ERR_INVALID_ARG, "null argument");
+    *difficulty = h->difficulty;
+    return BP_OK;
+}
+
+int bp_get_ranges(const bp_handle* h, double* obj_range, double* wrong_obj_range, double* max_obj_range) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    if (obj_range) *obj_range = h->obj_range;
+    if (wrong_obj_range) *wrong_obj_range = h->wrong_obj_range;
+    if (max_obj_range) *max_obj_range = h->max_obj_range;
+    return BP_OK;
+}
+
+int bp_set_ranges(bp_handle* h, double obj_range, double wrong_obj_range) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    h->obj_range = obj_range;
+    h->wrong_obj_range = wrong_obj_range;
+    return BP_OK;
+}
+
+int bp_get_state(bp_handle* h, bp_env_state* d_out, void* stream) {
+    if (!h || !d_out) return fail(BP_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    int rc = dispatch(h->env_id, [&](auto id) {
+        get_state_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, d_out);
+        return BP_OK;
+    });
+    if (rc != BP_OK) return rc;
+    CU(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_set_state(bp_handle* h, const bp_env_state* d_in, void* stream) {
+    if (!h || !d_in) return fail(BP_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    int rc = dispatch(h->env_id, [&](auto id) {
+        set_state_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, d_in);
+        return BP_OK;
+    });
+    if (rc != BP_OK) return rc;
+    CU(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_stats_ptr(bp_handle* h, double** d_stats) {
+    if (!h || !d_stats) return fail(BP_ERR_INVALID_ARG, "null argument");
+    *d_stats = h->d_stats;
+    return BP_OK;
+}
+
+int bp_stats_reset(bp_handle* h, void* stream) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * BP_NUM_STATS, (cudaStream_t)stream));
+    return BP_OK;
+}
+
+int bp_compute_reward(const float* d_ag, const float* d_g, int64_t n, int dimg, float* d_r, void* stream) {
+    if (n < 0 || dimg <= 0) return fail(BP_ERR_INVALID_ARG, "bad n or dimg");
+    if (n == 0) return BP_OK;
+    if (!d_ag || !d_g || !d_r) return fail(BP_ERR_INVALID_ARG, "null pointer");
+    compute_reward_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(d_ag, d_g, n, dimg, d_r);
+    CU(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_her_relabel(const float* d_ep_ag, const float* d_ep_g, int32_t B, int32_t T, int32_t dimg, int64_t n,
+                   float future_p, uint64_t seed, int64_t index_offset, int32_t* d_ep_idx, int32_t* d_t,
+                   int32_t* d_future_t, float* d_ag2, float* d_g, float* d_r, void* stream) {
+    if (B <= 0 || T <= 0 || dimg <= 0 || n < 0) return fail(BP_ERR_INVALID_ARG, "bad sizes");
+    if (n == 0) return BP_OK;
+    if (!d_ep_ag || !d_ep_g) return fail(BP_ERR_INVALID_ARG, "null episode store");
+    her_relabel_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(d_ep_ag, d_ep_g, B, T, dimg, n, future_p,
+                                                                      (uint32_t)seed, (uint32_t)(seed >> 32), index_offset,
+                                                                      d_ep_idx, d_t, d_future_t, d_ag2, d_g, d_r);
+    CU(cudaGetLastError());
+    return BP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+/*
+ * blockpuzzle_b200.h -- C-ABI of the B200-native batched gym_blocks environment
+ * hot path (libblockpuzzle_b200.so, built from blockpuzzle_gym_b200/csrc).
+ *
+ * The reference (matthew9671/BlockPuzzle-gym) has no FFI layer: the hot path sits
+ * behind the Python gym GoalEnv API.  Each entry point below names the reference
+ * interface it replaces (paths relative to /root/reference/gym_blocks); the
+ * Python binding a maintainer would add is shown in INTEGRATION.md and shipped
+ * in blockpuzzle_gym_b200/_lib.py.
+ *
+ * Conventions: plain C, no torch types.  Every function returns 0 on success or
+ * a negative bp_status; bp_last_error() returns the message of the calling
+ * thread's last failure.  Pointers named d_* are DEVICE pointers owned by the
+ * caller (e.g. torch tensors); h_* are HOST pointers.  `stream` is a
+ * cudaStream_t passed as void* (0 = legacy default stream).  Calls enqueue work
+ * on `stream` and return without synchronising unless stated otherwise.  One
+ * handle per (GPU, env id); a handle is not thread-safe.
+ */
+#ifndef BLOCKPUZZLE_B200_H
+#define BLOCKPUZZLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BP_ABI_VERSION 1
+
+typedef enum {
+    BP_OK = 0,
+    BP_ERR_INVALID_ARG = -1,
+    BP_ERR_CUDA = -2,
+    BP_ERR_NOT_IMPLEMENTED = -3, /* the reference method raises NotImplementedError / AttributeError */
+    BP_ERR_NO_DEVICE = -4
+} bp_status;
+
+/* env ids in the registration order of __init__.py:6-53 */
+typedef enum {
+    BP_GRIPPER_TOUCH = 0,                   /* 'GripperTouch-v0'                __init__.py:7  */
+    BP_BLOCKS_TOUCH = 1,                    /* 'BlocksTouch-v0'                 __init__.py:14 */
+    BP_TOPPLE_TOWER = 2,                    /* 'ToppleTower-v0'                 __init__.py:21 */
+    BP_BLOCKS_TOUCH_CURRICULUM = 3,         /* 'BlocksTouchCurriculum-v0'       __init__.py:28 */
+    BP_BLOCKS_TOUCH_CHOOSE = 4,             /* 'BlocksTouchChoose-v0'           __init__.py:35 */
+    BP_BLOCKS_TOUCH_CHOOSE_CURRICULUM = 5,  /* 'BlocksTouchChooseCurriculum-v0' __init__.py:42 */
+    BP_BLOCKS_TOUCH_VARIATION = 6,          /* 'BlocksTouchVariation-v0'        __init__.py:49 */
+    BP_NUM_ENV_IDS = 7
+} bp_env_id;
+
+#define BP_MAX_BLOCKS 4
+#define BP_MAX_DIMG 36
+#define BP_MAX_DIMO 87
+#define BP_MAX_EPISODE_STEPS 50 /* max_episode_steps, __init__.py:10 */
+#define BP_NUM_STATS 8
+
+/* indices into the stats vector (float64[BP_NUM_STATS]); this is the vector the
+ * single NCCL all-reduce carries (replaces mpi_moments, train.py:21-26) */
+enum {
+    BP_STAT_EPISODES = 0,   /* episodes that reached T = 50 */
+    BP_STAT_SUCCESSES = 1,  /* of those, is_success at the last step (rollout.py:163-167) */
+    BP_STAT_STEPS = 2,
+    BP_STAT_INVALID = 3,    /* non-finite action components (replaces the NaN restart, rollout.py:139-142) */
+    BP_STAT_REWARD_SUM = 4
+};
+
+/* Canonical per-env state record used by bp_get_state / bp_set_state (the
+ * bit-exact replay harness).  244 bytes, little endian, no padding. */
+typedef struct bp_env_state {
+    float grip_pos[3];
+    float grip_vel[3];
+    float finger_q[2];
+    float finger_qv[2];
+    float blk_pos[BP_MAX_BLOCKS][3];
+    float blk_cs[BP_MAX_BLOCKS][2];   /* yaw as (cos, sin) */
+    float blk_vel[BP_MAX_BLOCKS][3];
+    float blk_w[BP_MAX_BLOCKS];
+    int8_t ag[BP_MAX_DIMG];           /* touch matrix self.achieved_goal, fetch_env.py:78 */
+    int32_t num_objs;                 /* fetch_env.py:75 */
+    int32_t has_succeeded;            /* fetch_env.py:80 */
+    int32_t t;                        /* TimeLimit elapsed steps */
+    uint32_t episode;                 /* reset() calls so far */
+    uint32_t draws[2];                /* Philox draw counters: [0] self.np_random, [1] global np.random */
+} bp_env_state;
+
+typedef struct bp_handle bp_handle;
+
+/* ---- introspection ---- */
+int bp_abi_version(void);
+const char* bp_last_error(void);
+/* dims per env id (observation_space, robot_env.py:40-44) */
+int bp_env_dims(int env_id, int* dimo, int* dimg, int* nblocks);
+/* name <-> id of the ids registered in __init__.py:6-53 */
+int bp_env_id_from_name(const char* name);
+const char* bp_env_name(int env_id);
+
+/* ---- lifetime: replaces gym.make(env_name) x num_envs (rollout.py:33) ---- */
+/* Allocates the device state for `num_envs` envs of `env_id` on CUDA device
+ * `device`.  `env_index_offset` is the global index of this handle's env 0
+ * (multi-GPU sharding: results do not depend on how envs are split). */
+int bp_create(int env_id, int64_t num_envs, int device, uint64_t env_index_offset, bp_handle** out);
+int bp_destroy(bp_handle* h);
+int64_t bp_num_envs(const bp_handle* h);
+
+/* RolloutStudent.seed (rollout.py:206-210) + RobotEnv.seed (robot_env.py:53-55):
+ * env i gets seed + 1000 * (env_index_offset + i). */
+int bp_seed(bp_handle* h, uint64_t seed, void* stream);
+
+/* RobotEnv.reset (robot_env.py:71-82) for every env whose d_mask byte is
+ * non-zero (d_mask == NULL: all).  Outputs (any may be NULL): d_obs
+ * [B][dimo], d_ag [B][dimg], d_g [B][dimg]; rows of unselected envs are not
+ * written. */
+int bp_reset(bp_handle* h, const uint8_t* d_mask, float* d_obs, float* d_ag, float* d_g, void* stream);
+
+/* RobotEnv.step (robot_env.py:57-69) under TimeLimit, K fused steps per launch.
+ *   d_actions  [K][B][4] float32, or NULL: draw them in-kernel from Philox
+ *              stream 2 (the replay harness); d_actions_out (nullable) receives them.
+ *   d_obs      [K][B][dimo]   d_ag [K][B][dimg]   d_reward [K][B]
+ *   d_success  [K][B] float32 info['is_success'] (latched, fetch_env.py:275-281)
+ *   d_done     [K][B] uint8   TimeLimit done (nullable)
+ *   auto_reset != 0: an env that finishes step T = 50 is reset inside the kernel
+ *              after its outputs are written; its fresh reset observation goes to
+ *              d_reset_obs [B][dimo] / d_reset_ag [B][dimg] (nullable).
+ * Any output pointer may be NULL (that output is skipped). */
+int bp_step(bp_handle* h, const float* d_actions, int K, float* d_obs, float* d_ag, float* d_reward,
+            float* d_success, uint8_t* d_done, int auto_reset, float* d_reset_obs, float* d_reset_ag,
+            float* d_actions_out, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): actions are copied to the
+ * device, outputs copied back, chunked over envs and double-buffered on two
+ * internal streams.  Synchronous.  This is the end-to-end path a CPU trainer
+ * (rollout.py:121-131) uses. */
+int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, float* h_ag,
+                 float* h_reward, float* h_success, int auto_reset);
+
+/* BlocksTouchEnv.set_test / BlocksTouchChooseEnv.set_test / Variation.set_test
+ * (fetch_env.py:365-368, 443-446, 641-644); BP_ERR_NOT_IMPLEMENTED for
+ * GripperTouch / ToppleTower (fetch_env.py:100-101). */
+int bp_set_test(bp_handle* h, float* d_obs, float* d_ag, float* d_g, void* stream);
+
+/* increase_difficulty (fetch_env.py:351-358, 419-432, 623-630): *max_reached
+ * receives the python return value; BP_ERR_NOT_IMPLEMENTED where the reference raises. */
+int bp_increase_difficulty(bp_handle* h, int* max_reached);
+int bp_get_difficulty(const bp_handle* h, int* difficulty);           /* fetch_env.py:96-97 */
+/* direct access to the curriculum knobs (obj_range, wrong_obj_range, max_obj_range) */
+int bp_get_ranges(const bp_handle* h, double* obj_range, double* wrong_obj_range, double* max_obj_range);
+int bp_set_ranges(bp_handle* h, double obj_range, double wrong_obj_range);
+
+/* replay harness: canonical state records, [B] bp_env_state on the device */
+int bp_get_state(bp_handle* h, bp_env_state* d_out, void* stream);
+int bp_set_state(bp_handle* h, const bp_env_state* d_in, void* stream);
+
+/* statistics: d_stats float64[BP_NUM_STATS] lives in the handle; bp_stats_ptr
+ * returns its device address so the caller can all-reduce it in place. */
+int bp_stats_ptr(bp_handle* h, double** d_stats);
+int bp_stats_reset(bp_handle* h, void* stream);
+
+/* BlocksEnv.compute_reward (fetch_env.py:135-143), batched: d_ag, d_g [n][dimg]
+ * float32 -> d_r [n] float32 (-0.0 success, -1.0 otherwise).  Called through
+ * reward_fun (config.py:110-111). */
+int bp_compute_reward(const float* d_ag, const float* d_g, int64_t n, int dimg, float* d_r, void* stream);
+
+/* HER relabel + reward: baselines.her.her._sample_her_transitions [upstream],
+ * call sites config.py:121, ddpg.py:106,214-215.
+ *   d_ep_ag [B][T+1][dimg], d_ep_g [B][T][dimg]: the episode store
+ *   n transitions; transition i uses Philox counter (index_offset + i), stream 3
+ *   outputs (nullable): d_ep_idx, d_t, d_future_t int32 [n] (future_t = -1 when
+ *   not relabelled), d_ag2 [n][dimg], d_g [n][dimg], d_r [n]. */
+int bp_her_relabel(const float* d_ep_ag, const float* d_ep_g, int32_t B, int32_t T, int32_t dimg,
+                   int64_t n, float future_p, uint64_t seed, int64_t index_offset, int32_t* d_ep_idx,
+                   int32_t* d_t, int32_t* d_future_t, float* d_ag2, float* d_g, float* d_r, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

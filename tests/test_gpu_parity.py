@@ -1,0 +1,257 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the
+same seeded inputs.  Bar: bit-exact for integer state (touch matrix, latch, counters, Philox
+draw counters) AND bit-identical fp32 for every float (BlockPhys v1 fixes the op order)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import coracle  # noqa: E402
+
+
+def _make(name, B, seed=0, offset=0):
+    import blockpuzzle_gym_b200 as bpg
+    env = bpg.make_vec(name, B, device=0, seed=seed, env_index_offset=offset)
+    ref = coracle.OracleVecEnv(name, B, seed=seed, env_index_offset=offset)
+    return env, ref
+
+
+def _assert_state_equal(env, ref, ctx=""):
+    gs, rs = env.get_state(), ref.get_state()
+    for f in gs.dtype.names:
+        assert np.array_equal(gs[f].view(np.uint8), rs[f].view(np.uint8)), f"state field {f} differs {ctx}"
+
+
+@pytest.mark.parametrize("name", coracle.ENV_IDS)
+def test_reset_matches_oracle(name):
+    env, ref = _make(name, 257, seed=7)
+    for _ in range(3):
+        o = env.reset()
+        ro, rag, rg = ref.reset()
+        assert np.array_equal(o["observation"].cpu().numpy(), ro)
+        assert np.array_equal(o["achieved_goal"].cpu().numpy(), rag)
+        assert np.array_equal(o["desired_goal"].cpu().numpy(), rg)
+        _assert_state_equal(env, ref)
+
+
+@pytest.mark.parametrize("name", coracle.ENV_IDS)
+def test_step_by_step_replay(name):
+    """2 episodes of host-provided random actions, one launch per step, every output compared."""
+    B = 192
+    env, ref = _make(name, B, seed=11)
+    rng = np.random.RandomState(5)
+    env.reset(); ref.reset()
+    for ep in range(2):
+        for t in range(50):
+            a = rng.uniform(-1.3, 1.3, size=(B, 4)).astype(np.float32)  # some outside [-1,1]: exercises the clip
+            obs, r, done, info = env.step(torch.from_numpy(a).cuda())
+            o2, ag2, r2, s2, _, _ = ref.step(a)
+            assert np.array_equal(obs["observation"].cpu().numpy(), o2), (name, ep, t)
+            assert np.array_equal(obs["achieved_goal"].cpu().numpy(), ag2), (name, ep, t)
+            assert np.array_equal(r.cpu().numpy().view(np.uint32), r2.view(np.uint32)), "reward incl. sign of -0.0"
+            assert np.array_equal(info["is_success"].cpu().numpy(), s2)
+            assert bool(done.all().item()) == (t == 49)
+        _assert_state_equal(env, ref, f"after episode {ep}")
+        env.reset(); ref.reset()
+
+
+def test_4096_envs_fused_philox_replay():
+    """BASELINE config 2: 4096 batched envs, Philox-replayed bit-exact check (K fused steps, auto-reset)."""
+    B, K = 4096, 64
+    env, ref = _make("BlocksTouch-v0", B, seed=0)
+    env.reset(); ref.reset()
+    for launch in range(2):
+        out = env.step_fused(None, K=K, auto_reset=True, want_actions=True, want_reset_obs=True)
+        acts = out["actions"].cpu().numpy()
+        obs = out["observation"].cpu().numpy(); ag = out["achieved_goal"].cpu().numpy()
+        rew = out["reward"].cpu().numpy(); suc = out["is_success"].cpu().numpy()
+        for k in range(K):
+            a = ref.random_actions()
+            assert np.array_equal(a, acts[k])
+            o2, ag2, r2, s2, ro2, ra2 = ref.step(a, auto_reset=True)
+            assert np.array_equal(obs[k], o2), (launch, k)
+            assert np.array_equal(ag[k], ag2), (launch, k)
+            assert np.array_equal(rew[k].view(np.uint32), r2.view(np.uint32))
+            assert np.array_equal(suc[k], s2)
+        _assert_state_equal(env, ref, f"launch {launch}")
+    st = env.stats()
+    assert st["steps"] == 2 * K * B
+    assert st["episodes"] == ref.stats[0] and st["successes"] == ref.stats[1]
+
+
+@pytest.mark.parametrize("name", ["GripperTouch-v0", "ToppleTower-v0", "BlocksTouchChooseCurriculum-v0", "BlocksTouchVariation-v0"])
+def test_fused_replay_other_envs(name):
+    B, K = 512, 120
+    env, ref = _make(name, B, seed=3)
+    env.reset(); ref.reset()
+    out = env.step_fused(None, K=K, auto_reset=True, want_actions=True)
+    acts = out["actions"].cpu().numpy()
+    obs = out["observation"].cpu().numpy(); ag = out["achieved_goal"].cpu().numpy()
+    for k in range(K):
+        o2, ag2, r2, s2, _, _ = ref.step(acts[k], auto_reset=True)
+        assert np.array_equal(obs[k], o2), (name, k)
+        assert np.array_equal(ag[k], ag2), (name, k)
+    _assert_state_equal(env, ref)
+
+
+def test_10k_seeded_replay_episodes_state_hash():
+    """North-star bar: bit-exact state versus the oracle on 10k seeded replay episodes
+    (2048 envs x 5 episodes = 10240), compared through the canonical state records."""
+    B, episodes = 2048, 5
+    env, ref = _make("BlocksTouch-v0", B, seed=2024)
+    env.reset(); ref.reset()
+    for ep in range(episodes):
+        env.step_fused(None, K=50, auto_reset=True, outputs=())
+        ref.run_random(50)
+        _assert_state_equal(env, ref, f"episode {ep}")
+    assert env.stats()["episodes"] == B * episodes
+
+
+def test_sharding_is_invariant_to_env_offset():
+    """Multi-GPU contract: env i of a shard with offset o equals env o+i of the unsharded batch."""
+    import blockpuzzle_gym_b200 as bpg
+    full = bpg.make_vec("BlocksTouch-v0", 256, device=0, seed=9)
+    lo = bpg.make_vec("BlocksTouch-v0", 128, device=0, seed=9, env_index_offset=0)
+    hi = bpg.make_vec("BlocksTouch-v0", 128, device=0, seed=9, env_index_offset=128)
+    for e in (full, lo, hi):
+        e.reset()
+        e.step_fused(None, K=70, auto_reset=True, outputs=())
+    sf = full.get_state()
+    assert sf[:128].tobytes() == lo.get_state().tobytes()
+    assert sf[128:].tobytes() == hi.get_state().tobytes()
+
+
+@pytest.mark.parametrize("name", ["BlocksTouch-v0", "BlocksTouchCurriculum-v0", "BlocksTouchChooseCurriculum-v0", "BlocksTouchVariation-v0"])
+def test_set_test_and_curriculum(name):
+    env, ref = _make(name, 130, seed=21)
+    env.reset(); ref.reset()
+    o = env.set_test(); ro, rag, rg = ref.set_test()
+    assert np.array_equal(o["observation"].cpu().numpy(), ro)
+    assert np.array_equal(o["desired_goal"].cpu().numpy(), rg)
+    _assert_state_equal(env, ref, "after set_test")
+    for level in range(7):
+        assert env.increase_difficulty() == ref.increase_difficulty()
+        env.reset(); ref.reset()
+        _assert_state_equal(env, ref, f"level {level}")
+    assert env.get_difficulty() == ref.get_difficulty()
+    assert env.get_ranges()["obj_range"] == ref.get_obj_range()
+
+
+def test_not_implemented_paths():
+    import blockpuzzle_gym_b200 as bpg
+    for name in ("GripperTouch-v0", "ToppleTower-v0"):
+        env = bpg.make_vec(name, 8, device=0)
+        env.reset()
+        with pytest.raises(NotImplementedError):
+            env.set_test()
+        with pytest.raises(NotImplementedError):
+            env.increase_difficulty()
+    env = bpg.make_vec("BlocksTouchChoose-v0", 8, device=0)
+    with pytest.raises(NotImplementedError):  # AttributeError in the reference: no obj_range_step
+        env.increase_difficulty()
+
+
+def test_partial_reset_mask():
+    env, ref = _make("BlocksTouch-v0", 64, seed=4)
+    env.reset(); ref.reset()
+    a = np.zeros((64, 4), np.float32)
+    env.step(torch.from_numpy(a).cuda()); ref.step(a)
+    mask = torch.zeros(64, dtype=torch.uint8)
+    mask[::3] = 1
+    env.reset(mask=mask.cuda())
+    for i in range(0, 64, 3):
+        ref.reset_one(i)
+    _assert_state_equal(env, ref)
+
+
+def test_nan_actions_are_flagged_not_fatal():
+    env, ref = _make("BlocksTouch-v0", 32, seed=1)
+    env.reset(); ref.reset()
+    a = np.zeros((32, 4), np.float32)
+    a[3, 1] = np.nan
+    a[5, :] = np.inf
+    obs, r, done, info = env.step(torch.from_numpy(a).cuda())
+    o2, ag2, r2, s2, _, _ = ref.step(a)
+    assert np.isfinite(obs["observation"].cpu().numpy()).all()
+    assert np.array_equal(obs["observation"].cpu().numpy(), o2)
+    assert env.stats()["invalid"] == 1 == ref.stats[3]
+
+
+def test_compute_reward_matches_oracle_and_kats():
+    import blockpuzzle_gym_b200 as bpg
+    rng = np.random.RandomState(0)
+    for dimg in (9, 16, 25, 36):
+        ag = rng.randint(-1, 2, size=(1000, dimg)).astype(np.float32)
+        g = rng.randint(-1, 2, size=(1000, dimg)).astype(np.float32)
+        g[::7] = 0  # c == 0 rows
+        ag[::5] = g[::5] * g[::5] * g[::5]  # satisfied rows (ag == g where g != 0)
+        r = bpg.compute_reward(torch.from_numpy(ag).cuda(), torch.from_numpy(g).cuda(), None).cpu().numpy()
+        assert np.array_equal(r.view(np.uint32), coracle.compute_reward(ag, g).view(np.uint32))
+    # known answers derived from the in-tree code
+    goal = np.zeros(16, np.float32); goal[2 * 4 + 3] = goal[3 * 4 + 2] = 1
+    ag = -np.ones(16, np.float32)
+    assert bpg.compute_reward(ag, goal, None) == np.float32(-1.0)
+    ag[2 * 4 + 3] = ag[3 * 4 + 2] = 1
+    r = bpg.compute_reward(ag, goal, None)
+    assert r == 0 and np.signbit(r)
+    r3 = bpg.compute_reward(np.stack([ag] * 3), goal, None)  # broadcast goal like config.py:110-111
+    assert r3.shape == (3,) and (r3 == 0).all() and np.signbit(r3).all()
+    assert bpg.compute_reward(np.zeros((0, 16), np.float32), np.zeros((0, 16), np.float32), None).shape == (0,)
+
+
+def test_her_relabel_matches_oracle():
+    import blockpuzzle_gym_b200 as bpg
+    B, T, dimg = 300, 50, 16
+    env = bpg.make_vec("BlocksTouch-v0", B, device=0, seed=5)
+    o0 = env.reset()
+    out = env.step_fused(None, K=T, auto_reset=False)
+    ag = torch.cat([o0["achieved_goal"][None], out["achieved_goal"]], 0).transpose(0, 1).contiguous()  # [B,T+1,dimg]
+    g = env.goal()[:, None, :].expand(B, T, dimg).contiguous()
+    for strategy, fp in (("future", 0.8), ("none", 0.0)):
+        sampler = bpg.make_sample_her_transitions(strategy, 4, None, seed=77)
+        assert abs(sampler.future_p - fp) < 1e-12
+        n = 20000
+        tr = sampler(dict(ag=ag, g=g), n, index_offset=1000)
+        ref = coracle.her_relabel(ag.cpu().numpy(), g.cpu().numpy(), n, fp, 77, 1000)
+        for k in ("ep_idx", "t", "future_t", "ag_2", "g", "r"):
+            assert np.array_equal(tr[k].cpu().numpy(), ref[k]), (strategy, k)
+        if fp:
+            frac = float((tr["future_t"] >= 0).float().mean())
+            assert abs(frac - 0.8) < 0.02
+            ft = tr["future_t"][tr["future_t"] >= 0]
+            assert int(ft.max()) <= T and int((ft - tr["t"][tr["future_t"] >= 0]).min()) >= 1
+
+
+def test_step_host_matches_device_path():
+    import blockpuzzle_gym_b200 as bpg
+    B, K = 1000, 7
+    a = np.random.RandomState(3).uniform(-1, 1, size=(K, B, 4)).astype(np.float32)
+    e1 = bpg.make_vec("BlocksTouch-v0", B, device=0, seed=8); e1.reset()
+    e2 = bpg.make_vec("BlocksTouch-v0", B, device=0, seed=8); e2.reset()
+    d = e1.step_fused(torch.from_numpy(a).cuda(), auto_reset=True)
+    h = e2.step_host(a, auto_reset=True)
+    for k in ("observation", "achieved_goal", "reward", "is_success"):
+        assert np.array_equal(d[k].cpu().numpy(), h[k]), k
+    assert e1.get_state().tobytes() == e2.get_state().tobytes()
+
+
+def test_gym_single_env_surface():
+    """The object the reference gets from gym.make(env_name): reset/step/compute_reward/seed + TimeLimit."""
+    import blockpuzzle_gym_b200 as bpg
+    env = bpg.make("BlocksTouch-v0")
+    assert env._max_episode_steps == 50
+    env.seed(42)
+    ref = coracle.OracleVecEnv("BlocksTouch-v0", 1, seed=42)
+    obs = env.reset(); ro, rag, rg = ref.reset()
+    assert obs["observation"].dtype == np.float64 and obs["observation"].shape == (40,)
+    assert np.array_equal(obs["observation"].astype(np.float32), ro[0])
+    for t in range(50):
+        u = env.action_space.sample()
+        o, r, done, info = env.step(u)
+        o2, ag2, r2, s2, _, _ = ref.step(u[None])
+        assert np.array_equal(o["observation"].astype(np.float32), o2[0])
+        assert isinstance(r, np.float32) and r == r2[0]
+        assert info["is_success"] == bool(s2[0])
+        assert done == (t == 49)
+        assert env.compute_reward(o["achieved_goal"], o["desired_goal"], info) == r
