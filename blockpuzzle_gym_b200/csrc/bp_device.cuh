@@ -659,16 +659,23 @@ __device__ __forceinline__ void env_reset(Env<Cfg<ID>::NB>& e, const Ranges& rg)
     e.episode = ep + 1;
 }
 
+// -(d != c).astype(float32): -1.0 or -0.0 (appendix A7).  Stored as an integer bit pattern: nvcc
+// folds `cond ? -1.0f : -0.0f` (even through __uint_as_float) into an int->float convert that
+// loses the sign of zero.
+__device__ __forceinline__ void store_reward(float* dst, bool fail) {
+    *reinterpret_cast<uint32_t*>(dst) = fail ? 0xbf800000u : 0x80000000u;
+}
+
 // reward of the env's own touch matrix against its goal: fetch_env.py:135-143 on
 // ag in {-1,0,1}: d = sum(ag*g), c = count_nonzero(g); both symmetric entries counted.
 template <int ID>
-__device__ __forceinline__ float env_reward(uint32_t now, uint32_t ever) {
+__device__ __forceinline__ bool env_reward_fail(uint32_t now, uint32_t ever) {
     using C = Cfg<ID>;
     int sp = __popc(now & C::P) - __popc(~ever & C::P);   // sum of ag over the +1 goal pairs
     int sm = __popc(now & C::M) - __popc(~ever & C::M);   // sum of ag over the -1 goal pairs
     int d = 2 * (sp - sm);
     int c = 2 * (__popc(C::P) + __popc(C::M));
-    return (d != c) ? -1.0f : -0.0f;
+    return d != c;
 }
 
 // value of touch-matrix entry (i, j) as the reference stores it
@@ -750,9 +757,10 @@ __device__ __forceinline__ void env_write_goal(Store&& put) {
         }
 }
 
-// RobotEnv.step (robot_env.py:57-69) for one env; returns the reward, updates latch and t.
+// RobotEnv.step (robot_env.py:57-69) for one env; returns true when the reward is -1 (false: -0.0),
+// updates latch and t.
 template <int ID>
-__device__ __forceinline__ float env_step(Env<Cfg<ID>::NB>& e, float a0, float a1, float a2, float a3, int& invalid) {
+__device__ __forceinline__ bool env_step(Env<Cfg<ID>::NB>& e, float a0, float a1, float a2, float a3, int& invalid) {
     using C = Cfg<ID>;
     float a[4] = {a0, a1, a2, a3};
 #pragma unroll
@@ -765,10 +773,10 @@ __device__ __forceinline__ float env_step(Env<Cfg<ID>::NB>& e, float a0, float a
     // _step_callback fetch_env.py:148-167: 1 -> 0 downgrade, then contacts -> 1
     e.touch_now = e.contacts;
     e.touch_ever |= e.contacts;
-    float r = env_reward<ID>(e.touch_now, e.touch_ever);
-    if (r == 0.0f) e.succ = 1;  // _is_success latch, fetch_env.py:275-281
+    const bool fail = env_reward_fail<ID>(e.touch_now, e.touch_ever);
+    if (!fail) e.succ = 1;  // _is_success latch (r == 0), fetch_env.py:275-281
     e.t += 1;
-    return r;
+    return fail;
 }
 
 }  // namespace bp

@@ -182,14 +182,14 @@ __global__ void __launch_bounds__(128) step_kernel_simple(uint32_t* st, StepArgs
             }
             if (p.actions_out) reinterpret_cast<float4*>(p.actions_out)[row] = a;
             int inv = 0;
-            float r = env_step<ID>(e, a.x, a.y, a.z, a.w, inv);
+            const bool fail = env_step<ID>(e, a.x, a.y, a.z, a.w, inv);
             if (p.obs) write_row_obs<ID>(e, p.obs + row * C::DIMO);
             if (p.ag) write_row_ag<ID>(e, p.ag + row * C::DIMG);
-            if (p.reward) p.reward[row] = r;
+            if (p.reward) store_reward(p.reward + row, fail);
             if (p.success) p.success[row] = (float)e.succ;
             const bool done = e.t >= kT;
             if (p.done) p.done[row] = done ? 1 : 0;
-            n_st += 1.f; n_inv += (float)inv; r_sum += r;
+            n_st += 1.f; n_inv += (float)inv; r_sum += fail ? -1.f : 0.f;
             if (done) {
                 n_ep += 1.f; n_su += (float)e.succ;
                 if (p.auto_reset) {
@@ -300,7 +300,7 @@ __global__ void compute_reward_kernel(const float* __restrict__ ag, const float*
             c += (y != 0.0f);
         }
     }
-    r[i] = (d != (float)c) ? -1.0f : -0.0f;
+    store_reward(r + i, d != (float)c);
 }
 
 // HER relabel + reward (baselines.her.her._sample_her_transitions [upstream]; config.py:107-123)
@@ -338,7 +338,7 @@ __global__ void her_relabel_kernel(const float* __restrict__ ep_ag, const float*
             if (ag2_out) ag2_out[i * dimg + k] = x;
         }
     }
-    if (r_out) r_out[i] = (d != (float)c) ? -1.0f : -0.0f;
+    if (r_out) store_reward(r_out + i, d != (float)c);
     if (ep_idx) ep_idx[i] = e;
     if (t_idx) t_idx[i] = t;
     if (fut_t) fut_t[i] = her ? ft : -1;

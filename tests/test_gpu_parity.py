@@ -20,7 +20,8 @@ def _make(name, B, seed=0, offset=0):
 def _assert_state_equal(env, ref, ctx=""):
     gs, rs = env.get_state(), ref.get_state()
     for f in gs.dtype.names:
-        assert np.array_equal(gs[f].view(np.uint8), rs[f].view(np.uint8)), f"state field {f} differs {ctx}"
+        a, b = np.ascontiguousarray(gs[f]), np.ascontiguousarray(rs[f])
+        assert a.tobytes() == b.tobytes(), f"state field {f} differs {ctx}"
 
 
 @pytest.mark.parametrize("name", coracle.ENV_IDS)
