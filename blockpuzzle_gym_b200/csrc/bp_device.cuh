@@ -1,7 +1,7 @@
 // bp_device.cuh -- device-side implementation of the gym_blocks env hot path for sm_100a.
 //
-// Everything here is written for one thread = one env with the whole env state in
-// registers; the kernels in bp_kernels.cu decide how envs are tiled over warps.
+// One thread advances one env: the gripper in registers, the cubes in a private shared-memory
+// column; the kernels in bp_kernels.cu decide how envs are tiled over warps.
 // Arithmetic follows the BlockPhys v1 specification of DESIGN.md exactly (fp32,
 // every operation individually rounded: compile with -fmad=false), so integer
 // state is bit-exact and float state bit-identical against the CPU oracle.
@@ -176,14 +176,7 @@ struct Env {
     int succ;
     uint32_t episode, draws0, draws1;
     uint32_t key0, key1;             // Philox key = this env's seed
-};
-
-// per-substep scratch
-template <int NB>
-struct Sub {
-    float ox[NB], oy[NB], oz[NB], dth[NB];
-    bool sup[NB];
-    float gox, goy, qo[2], closed[2];
+    uint32_t priv;                   // kernel-private: bit 31 = cubes on a fixed point, bits 0-14 = their contact pairs
 };
 
 template <int NB>
@@ -203,6 +196,36 @@ __device__ __forceinline__ void sim_init(Env<NB>& e, bool tower) {
     e.contacts = 0;
 }
 
+// ---------------------------------------------------------------- BlockPhys v1: sim.step()
+// The hot physics is written as compact loops over one env's cubes held in a PRIVATE shared-memory
+// column (field f of cube b at p[(9*b+f)*STRIDE]; per-substep scratch behind it), the gripper in
+// registers.  Loops are deliberately not unrolled: the whole step must stay inside the instruction
+// cache (a fully unrolled version is >100 KB of SASS and stalls on instruction fetch).
+struct Blk { float x, y, z, c, s, vx, vy, vz, w; };
+struct Grip { float g[3], gv[3], q[2], qv[2]; };
+struct GripSub { float gox, goy, qo[2], closed[2]; };
+
+template <int NB, int STRIDE>
+struct Col {
+    float* p;
+    __device__ __forceinline__ Blk load(int b) const {
+        const float* q = p + 9 * b * STRIDE;
+        return Blk{q[0], q[STRIDE], q[2 * STRIDE], q[3 * STRIDE], q[4 * STRIDE], q[5 * STRIDE], q[6 * STRIDE], q[7 * STRIDE], q[8 * STRIDE]};
+    }
+    __device__ __forceinline__ void store(int b, const Blk& k) const {
+        float* q = p + 9 * b * STRIDE;
+        q[0] = k.x; q[STRIDE] = k.y; q[2 * STRIDE] = k.z; q[3 * STRIDE] = k.c; q[4 * STRIDE] = k.s;
+        q[5 * STRIDE] = k.vx; q[6 * STRIDE] = k.vy; q[7 * STRIDE] = k.vz; q[8 * STRIDE] = k.w;
+    }
+    __device__ __forceinline__ void store_pose(int b, const Blk& k) const {
+        float* q = p + 9 * b * STRIDE;
+        q[0] = k.x; q[STRIDE] = k.y; q[2 * STRIDE] = k.z; q[3 * STRIDE] = k.c; q[4 * STRIDE] = k.s;
+    }
+    // scratch: start-of-substep position (0..2) and accumulated yaw change (3)
+    __device__ __forceinline__ float& scr(int b, int f) const { return p[(9 * NB + 4 * b + f) * STRIDE]; }
+    static constexpr int kFields = 13 * NB;
+};
+
 __device__ __forceinline__ void rot_apply(float& c, float& s, float dth) {
     float c2 = c - s * dth;
     float s2 = s + c * dth;
@@ -214,27 +237,35 @@ __device__ __forceinline__ void rot_apply(float& c, float& s, float dth) {
 struct Rect { float x, y, c, s, hx, hy; };
 struct Sat { float ov[4], proj[4], rtA[4], rtB[4]; };
 
-__device__ __forceinline__ void sat_eval(const Rect& A, const Rect& B, Sat& o) {
-    float cr = A.c * B.c + A.s * B.s;
-    float sr = A.c * B.s - A.s * B.c;
+// Separating-axis overlaps of two rectangles; axes 0 = A.u, 1 = A.v, 2 = B.u, 3 = B.v.  Evaluated
+// axis by axis and abandoned (returns false) as soon as one overlap is <= -margin or `ovz` already
+// is: the pair then cannot be in contact, exactly as min(ovz, ov[0..3]) > -margin would decide.
+// AA: A is axis-aligned (c = 1, s = 0), which makes cr = B.c, sr = B.s, proj[0] = dx, proj[1] = dy exactly.
+template <bool AA>
+__device__ __forceinline__ bool sat_eval(const Rect& A, const Rect& B, Sat& o) {
+    float cr = AA ? B.c : A.c * B.c + A.s * B.s;
+    float sr = AA ? B.s : A.c * B.s - A.s * B.c;
     float C = fabsf(cr), S = fabsf(sr);
     float dx = B.x - A.x, dy = B.y - A.y;
     float RBu = B.hx * C + B.hy * S;
+    o.proj[0] = AA ? dx : dx * A.c + dy * A.s;
+    o.ov[0] = (A.hx + RBu) - fabsf(o.proj[0]);
+    if (!(o.ov[0] > -kMargin)) return false;
     float RBv = B.hx * S + B.hy * C;
+    o.proj[1] = AA ? dy : dy * A.c - dx * A.s;
+    o.ov[1] = (A.hy + RBv) - fabsf(o.proj[1]);
+    if (!(o.ov[1] > -kMargin)) return false;
     float RAu = A.hx * C + A.hy * S;
     float RAv = A.hx * S + A.hy * C;
-    o.proj[0] = dx * A.c + dy * A.s;
-    o.proj[1] = dy * A.c - dx * A.s;
     o.proj[2] = dx * B.c + dy * B.s;
     o.proj[3] = dy * B.c - dx * B.s;
-    o.ov[0] = (A.hx + RBu) - fabsf(o.proj[0]);
-    o.ov[1] = (A.hy + RBv) - fabsf(o.proj[1]);
     o.ov[2] = (RAu + B.hx) - fabsf(o.proj[2]);
     o.ov[3] = (RAv + B.hy) - fabsf(o.proj[3]);
     o.rtA[0] = A.hy; o.rtB[0] = RBv;
     o.rtA[1] = A.hx; o.rtB[1] = RBu;
     o.rtA[2] = RAv;  o.rtB[2] = B.hy;
     o.rtA[3] = RAu;  o.rtB[3] = B.hx;
+    return true;
 }
 
 // argmin with first-wins ties; returns the value through `mn`
@@ -275,43 +306,48 @@ __device__ __forceinline__ bool over_table(float x, float y) {
     return fabsf(x - kTblX) <= kTblHX && fabsf(y - kTblY) <= kTblHY;
 }
 
-template <int NB>
-__device__ __forceinline__ void collide_finger_block(Env<NB>& e, Sub<NB>& st, const int f, const int bi) {
+// finger f (0: +y, 1: -y) against cube b (index bi); ox/oy: the cube's start-of-substep position
+__device__ __forceinline__ void collide_finger_block(Grip& e, GripSub& st, const int f, Blk& b, const float ox, const float oy,
+                                                     float& dth_acc, bool& rotated, uint32_t& sup, uint32_t& contacts, const int bi) {
     const float sgn = f == 0 ? 1.0f : -1.0f;
-    Rect A{e.g[0], e.g[1] + sgn * (kFY0 + e.q[f]), 1.0f, 0.0f, kFX, kFY};
+    const float qf = f == 0 ? e.q[0] : e.q[1];
+    Rect A{e.g[0], e.g[1] + sgn * (kFY0 + qf), 1.0f, 0.0f, kFX, kFY};
     float az = e.g[2] + kFZOff;
-    Rect B{e.px[bi], e.py[bi], e.c[bi], e.s[bi], kHB, kHB};
-    float dz = e.pz[bi] - az;
+    Rect B{b.x, b.y, b.c, b.s, kHB, kHB};
+    float dz = b.z - az;
     float ovz = (kFZ + kHB) - fabsf(dz);
+    if (!(ovz > -kMargin)) return;
     Sat o;
-    sat_eval(A, B, o);
+    if (!sat_eval<true>(A, B, o)) return;
     float minxy;
     int k = sat_argmin(o, minxy);
     float minov = ovz < minxy ? ovz : minxy;
     if (!(minov > -kMargin)) return;
-    e.contacts |= pair_bit(0, 2) << bi;  // pair (0, bi+2): consecutive pair indices
+    contacts |= pair_bit(0, 2) << bi;  // pair (0, bi+2): any "finger" geom -> object 0 (fetch_env.py:111-112)
     if (!(minov > 0.0f)) return;
     if (ovz <= minxy) {
         if (dz >= 0.0f) {
-            e.pz[bi] = az + (kFZ + kHB);
-            st.sup[bi] = true;
+            b.z = az + (kFZ + kHB);
+            sup |= 1u << bi;
         } else {
-            e.g[2] = (e.pz[bi] + (kFZ + kHB)) - kFZOff;
+            e.g[2] = (b.z + (kFZ + kHB)) - kFZOff;
             if (e.gv[2] < 0.0f) e.gv[2] = 0.0f;
         }
         return;
     }
     float delta = minxy;
+    float q_now = qf;
     if (k == 1) {
         bool inner = (f == 0) ? (o.proj[1] < 0.0f) : (o.proj[1] > 0.0f);
         if (inner) {
-            float yield = delta < st.closed[f] ? delta : st.closed[f];
-            float room = kQMax - e.q[f];
+            const float closed = f == 0 ? st.closed[0] : st.closed[1];
+            float yield = delta < closed ? delta : closed;
+            float room = kQMax - qf;
             if (yield > room) yield = room;
             if (yield > 0.0f) {
-                e.q[f] = e.q[f] + yield;
-                e.qv[f] = 0.0f;
-                st.closed[f] = st.closed[f] - yield;
+                q_now = qf + yield;
+                if (f == 0) { e.q[0] = q_now; e.qv[0] = 0.0f; st.closed[0] = closed - yield; }
+                else { e.q[1] = q_now; e.qv[1] = 0.0f; st.closed[1] = closed - yield; }
                 delta = delta - yield;
             }
             if (!(delta > 0.0f)) return;
@@ -319,50 +355,55 @@ __device__ __forceinline__ void collide_finger_block(Env<NB>& e, Sub<NB>& st, co
     }
     float nx, ny, rnA, rnB;
     sat_contact(A, B, o, k, nx, ny, rnA, rnB);
+    const float qo = f == 0 ? st.qo[0] : st.qo[1];
     float fdx = e.g[0] - st.gox;
-    float fdy = (e.g[1] - st.goy) + sgn * (e.q[f] - st.qo[f]);
-    float rel = ((e.px[bi] - st.ox[bi]) - fdx) * nx + ((e.py[bi] - st.oy[bi]) - fdy) * ny;
+    float fdy = (e.g[1] - st.goy) + sgn * (q_now - qo);
+    float rel = ((b.x - ox) - fdx) * nx + ((b.y - oy) - fdy) * ny;
     float cap = kDepen - rel;
     float lam = delta < cap ? delta : cap;
     if (!(lam > 0.0f)) return;
     float D = 1.0f + kIInv * (rnB * rnB);
     float l = lam / D;
-    e.px[bi] = e.px[bi] + nx * l;
-    e.py[bi] = e.py[bi] + ny * l;
+    b.x = b.x + nx * l;
+    b.y = b.y + ny * l;
     float dth = (kIInv * rnB) * l;
     if (dth != 0.0f) {
-        rot_apply(e.c[bi], e.s[bi], dth);
-        st.dth[bi] = st.dth[bi] + dth;
+        rot_apply(b.c, b.s, dth);
+        dth_acc = dth_acc + dth;
+        rotated = true;
     }
 }
 
-template <int NB>
-__device__ __forceinline__ void collide_block_block(Env<NB>& e, Sub<NB>& st, const int i, const int j) {
-    Rect A{e.px[i], e.py[i], e.c[i], e.s[i], kHB, kHB};
-    Rect B{e.px[j], e.py[j], e.c[j], e.s[j], kHB, kHB};
-    float dz = e.pz[j] - e.pz[i];
+// cubes i < j; aox.. are their start-of-substep positions
+__device__ __forceinline__ void collide_block_block(Blk& a, const float aox, const float aoy, float& adth,
+                                                    Blk& b, const float box, const float boy, float& bdth,
+                                                    bool& rotated, uint32_t& sup, uint32_t& contacts, const int i, const int j) {
+    Rect A{a.x, a.y, a.c, a.s, kHB, kHB};
+    Rect B{b.x, b.y, b.c, b.s, kHB, kHB};
+    float dz = b.z - a.z;
     float ovz = kTwoHB - fabsf(dz);
+    if (!(ovz > -kMargin)) return;
     Sat o;
-    sat_eval(A, B, o);
+    if (!sat_eval<false>(A, B, o)) return;
     float minxy;
     int k = sat_argmin(o, minxy);
     float minov = ovz < minxy ? ovz : minxy;
     if (!(minov > -kMargin)) return;
-    e.contacts |= 1u << pair_index(i + 2, j + 2);
+    contacts |= 1u << pair_index(i + 2, j + 2);  // "objectK" -> K + 2 (fetch_env.py:115-116)
     if (!(minov > 0.0f)) return;
     int pin = 0;
     if (ovz <= minxy) {
         if (dz >= 0.0f) {
             if (fabsf(o.proj[0]) <= kHB && fabsf(o.proj[1]) <= kHB) {
-                e.pz[j] = e.pz[i] + kTwoHB;
-                st.sup[j] = true;
+                b.z = a.z + kTwoHB;
+                sup |= 1u << j;
                 return;
             }
             pin = 1;
         } else {
             if (fabsf(o.proj[2]) <= kHB && fabsf(o.proj[3]) <= kHB) {
-                e.pz[i] = e.pz[j] + kTwoHB;
-                st.sup[i] = true;
+                a.z = b.z + kTwoHB;
+                sup |= 1u << i;
                 return;
             }
             pin = 2;
@@ -370,7 +411,7 @@ __device__ __forceinline__ void collide_block_block(Env<NB>& e, Sub<NB>& st, con
     }
     float nx, ny, rnA, rnB;
     sat_contact(A, B, o, k, nx, ny, rnA, rnB);
-    float rel = ((e.px[j] - st.ox[j]) - (e.px[i] - st.ox[i])) * nx + ((e.py[j] - st.oy[j]) - (e.py[i] - st.oy[i])) * ny;
+    float rel = ((b.x - box) - (a.x - aox)) * nx + ((b.y - boy) - (a.y - aoy)) * ny;
     float cap = kDepen - rel;
     float lam = minxy < cap ? minxy : cap;
     if (!(lam > 0.0f)) return;
@@ -379,19 +420,19 @@ __device__ __forceinline__ void collide_block_block(Env<NB>& e, Sub<NB>& st, con
     float D = (wA + wB) + kIInv * (wA * (rnA * rnA) + wB * (rnB * rnB));
     float l = lam / D;
     float lA = wA * l, lB = wB * l;
-    e.px[i] = e.px[i] - nx * lA;
-    e.py[i] = e.py[i] - ny * lA;
-    e.px[j] = e.px[j] + nx * lB;
-    e.py[j] = e.py[j] + ny * lB;
+    a.x = a.x - nx * lA;
+    a.y = a.y - ny * lA;
+    b.x = b.x + nx * lB;
+    b.y = b.y + ny * lB;
     float dthA = -((kIInv * rnA) * lA);
     float dthB = (kIInv * rnB) * lB;
-    if (dthA != 0.0f) { rot_apply(e.c[i], e.s[i], dthA); st.dth[i] = st.dth[i] + dthA; }
-    if (dthB != 0.0f) { rot_apply(e.c[j], e.s[j], dthB); st.dth[j] = st.dth[j] + dthB; }
+    if (dthA != 0.0f) { rot_apply(a.c, a.s, dthA); adth = adth + dthA; rotated = true; }
+    if (dthB != 0.0f) { rot_apply(b.c, b.s, dthB); bdth = bdth + dthB; rotated = true; }
 }
 
 // the gripper part of one substep (steps 1-2 of the spec)
-template <int NB, bool BG>
-__device__ __forceinline__ void substep_gripper(Env<NB>& e, Sub<NB>& st, const float m[3], const float ctrl[2]) {
+template <bool BG>
+__device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const float m[3], const float ctrl[2]) {
     st.closed[0] = st.closed[1] = 0.0f;
     st.gox = e.g[0]; st.goy = e.g[1];
     st.qo[0] = e.q[0]; st.qo[1] = e.q[1];
@@ -420,92 +461,141 @@ __device__ __forceinline__ void substep_gripper(Env<NB>& e, Sub<NB>& st, const f
     }
 }
 
-// the cube part of one substep (steps 3-5 of the spec)
-template <int NB>
-__device__ __forceinline__ void substep_blocks(Env<NB>& e, Sub<NB>& st) {
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        if (i < e.nb) {
-            st.ox[i] = e.px[i]; st.oy[i] = e.py[i]; st.oz[i] = e.pz[i];
-            st.dth[i] = 0.0f;
-            st.sup[i] = false;
-            e.vz[i] = e.vz[i] - kGH;
-            e.px[i] = e.px[i] + e.vx[i] * kH;
-            e.py[i] = e.py[i] + e.vy[i] * kH;
-            e.pz[i] = e.pz[i] + e.vz[i] * kH;
-            if (e.w[i] != 0.0f) {
-                float dth = e.w[i] * kH;
-                rot_apply(e.c[i], e.s[i], dth);
-                st.dth[i] = dth;
+// the cube part of one substep (steps 3-5 of the spec).  Returns true when the substep left every
+// cube bit-for-bit unchanged (all at rest before and after, nothing moved or rotated): a fixed point.
+template <int NB, int STRIDE>
+__device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB, STRIDE> col, const int nb, uint32_t& contacts) {
+    uint32_t sup = 0;
+    bool rest = true, rotated = false;
+    contacts = 0;
+    // 3. predict + 4a. table / floor support (both only depend on the cube itself)
+#pragma unroll 1
+    for (int i = 0; i < nb; ++i) {
+        Blk b = col.load(i);
+        rest = rest && b.vx == 0.0f && b.vy == 0.0f && b.vz == 0.0f && b.w == 0.0f;
+        col.scr(i, 0) = b.x; col.scr(i, 1) = b.y; col.scr(i, 2) = b.z;
+        float dth = 0.0f;
+        b.vz = b.vz - kGH;
+        b.x = b.x + b.vx * kH;
+        b.y = b.y + b.vy * kH;
+        b.z = b.z + b.vz * kH;
+        if (b.w != 0.0f) {
+            dth = b.w * kH;
+            rot_apply(b.c, b.s, dth);
+            rotated = true;
+        }
+        col.scr(i, 3) = dth;
+        if (over_table(b.x, b.y)) {
+            if (b.z - kZRest < kMargin) contacts |= pair_bit(1, 2) << i;  // "table" -> 1 (fetch_env.py:113-114)
+            if (b.z < kZRest) { b.z = kZRest; sup |= 1u << i; }
+        } else if (b.z < kZFloor) {
+            b.z = kZFloor;  // floor0 maps to None: no touch entry
+            sup |= 1u << i;
+        }
+        col.store_pose(i, b);
+    }
+    // 4b. fingers vs cubes
+#pragma unroll 1
+    for (int i = 0; i < nb; ++i) {
+        Blk b = col.load(i);
+        const float ox = col.scr(i, 0), oy = col.scr(i, 1);
+        float dth = col.scr(i, 3);
+#pragma unroll 1
+        for (int f = 0; f < 2; ++f) collide_finger_block(e, st, f, b, ox, oy, dth, rotated, sup, contacts, i);
+        col.scr(i, 3) = dth;
+        col.store_pose(i, b);
+    }
+    // 4c. cube pairs
+#pragma unroll 1
+    for (int i = 0; i + 1 < nb; ++i) {
+#pragma unroll 1
+        for (int j = i + 1; j < nb; ++j) {
+            Blk a = col.load(i), b = col.load(j);
+            float adth = col.scr(i, 3), bdth = col.scr(j, 3);
+            collide_block_block(a, col.scr(i, 0), col.scr(i, 1), adth, b, col.scr(j, 0), col.scr(j, 1), bdth, rotated, sup, contacts, i, j);
+            col.scr(i, 3) = adth; col.scr(j, 3) = bdth;
+            col.store_pose(i, a); col.store_pose(j, b);
+        }
+    }
+    // 4d. fingers vs table
+    if (over_table(e.g[0], e.g[1]) && e.g[2] - kGZMin < kMargin) contacts |= pair_bit(0, 1);
+    // 5. velocities from the position change, then Coulomb friction on supported cubes
+    bool same = rest && !rotated;
+#pragma unroll 1
+    for (int i = 0; i < nb; ++i) {
+        Blk b = col.load(i);
+        const float ox = col.scr(i, 0), oy = col.scr(i, 1), oz = col.scr(i, 2);
+        same = same && __float_as_uint(b.x) == __float_as_uint(ox) && __float_as_uint(b.y) == __float_as_uint(oy) &&
+               __float_as_uint(b.z) == __float_as_uint(oz);
+        b.vx = clampf((b.x - ox) * kInvH, -kVMax, kVMax);
+        b.vy = clampf((b.y - oy) * kInvH, -kVMax, kVMax);
+        b.vz = clampf((b.z - oz) * kInvH, -kVMax, kVMax);
+        b.w = clampf(col.scr(i, 3) * kInvH, -kWMax, kWMax);
+        if (sup >> i & 1u) {
+            float sp2 = b.vx * b.vx + b.vy * b.vy;
+            if (sp2 <= kFr * kFr) {
+                b.vx = 0.0f; b.vy = 0.0f;
+            } else {
+                float sp = sqrtf(sp2);
+                float kf = (sp - kFr) / sp;
+                b.vx = b.vx * kf;
+                b.vy = b.vy * kf;
             }
+            if (fabsf(b.w) <= kFrW) b.w = 0.0f;
+            else b.w = b.w > 0.0f ? b.w - kFrW : b.w + kFrW;
         }
+        same = same && b.vx == 0.0f && b.vy == 0.0f && b.vz == 0.0f && b.w == 0.0f;
+        col.store(i, b);
     }
-    e.contacts = 0;
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        if (i < e.nb) {
-            if (over_table(e.px[i], e.py[i])) {
-                if (e.pz[i] - kZRest < kMargin) e.contacts |= pair_bit(1, 2) << i;
-                if (e.pz[i] < kZRest) { e.pz[i] = kZRest; st.sup[i] = true; }
-            } else if (e.pz[i] < kZFloor) {
-                e.pz[i] = kZFloor;
-                st.sup[i] = true;
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        if (i < e.nb) {
-            collide_finger_block<NB>(e, st, 0, i);
-            collide_finger_block<NB>(e, st, 1, i);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i)
-#pragma unroll
-        for (int j = i + 1; j < NB; ++j)
-            if (j < e.nb) collide_block_block<NB>(e, st, i, j);
-    if (over_table(e.g[0], e.g[1]) && e.g[2] - kGZMin < kMargin) e.contacts |= pair_bit(0, 1);
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-        if (i < e.nb) {
-            e.vx[i] = clampf((e.px[i] - st.ox[i]) * kInvH, -kVMax, kVMax);
-            e.vy[i] = clampf((e.py[i] - st.oy[i]) * kInvH, -kVMax, kVMax);
-            e.vz[i] = clampf((e.pz[i] - st.oz[i]) * kInvH, -kVMax, kVMax);
-            e.w[i] = clampf(st.dth[i] * kInvH, -kWMax, kWMax);
-            if (st.sup[i]) {
-                float sp2 = e.vx[i] * e.vx[i] + e.vy[i] * e.vy[i];
-                if (sp2 <= kFr * kFr) {
-                    e.vx[i] = 0.0f; e.vy[i] = 0.0f;
-                } else {
-                    float sp = sqrtf(sp2);
-                    float kf = (sp - kFr) / sp;
-                    e.vx[i] = e.vx[i] * kf;
-                    e.vy[i] = e.vy[i] * kf;
-                }
-                if (fabsf(e.w[i]) <= kFrW) e.w[i] = 0.0f;
-                else e.w[i] = e.w[i] > 0.0f ? e.w[i] - kFrW : e.w[i] + kFrW;
-            }
-        }
-    }
+    return same;
 }
 
-// _set_action (fetch_env.py:170-185, after the clip of robot_env.py:58) + sim.step() (robot_env.py:60)
-template <int NB, bool BG>
-__device__ __forceinline__ void sim_step(Env<NB>& e, const float a[4]) {
-    float m[3], ctrl[2];
+// mocap target and finger actuator targets from the clipped action (fetch_env.py:170-185)
+template <bool BG>
+__device__ __forceinline__ void action_targets(const Grip& e, const float a[4], float m[3], float ctrl[2]) {
     m[0] = clampf(e.g[0] + a[0] * kPosScale, kWsXLo, kWsXHi);
     m[1] = clampf(e.g[1] + a[1] * kPosScale, kWsYLo, kWsYHi);
     m[2] = clampf(e.g[2] + a[2] * kPosScale, kGZMin, kWsZHi);
     float ga = BG ? 0.0f : a[3];
     ctrl[0] = clampf(e.q[0] + ga, 0.0f, kCtrlMax);
     ctrl[1] = clampf(e.q[1] + ga, 0.0f, kCtrlMax);
+}
+
+// _set_action (fetch_env.py:170-185, after the clip of robot_env.py:58) + sim.step() (robot_env.py:60).
+// Returns whether the cubes ended the step on an exact fixed point; `contacts` = pairs of the last substep.
+template <int NB, int STRIDE, bool BG>
+__device__ __forceinline__ bool sim_step_col(Grip& g, const float a[4], const Col<NB, STRIDE> col, const int nb, uint32_t& contacts) {
+    float m[3], ctrl[2];
+    action_targets<BG>(g, a, m, ctrl);
+    bool still = false;
 #pragma unroll 1
     for (int sub = 0; sub < kNSub; ++sub) {
-        Sub<NB> st;
-        substep_gripper<NB, BG>(e, st, m, ctrl);
-        substep_blocks<NB>(e, st);
+        GripSub st;
+        substep_gripper<BG>(g, st, m, ctrl);
+        still = substep_cubes<NB, STRIDE>(g, st, col, nb, contacts);
     }
+    return still;
+}
+
+// contact bits that involve the gripper (object 0)
+__host__ __device__ constexpr uint32_t gripper_pair_mask() {
+    return pair_bit(0, 1) | pair_bit(0, 2) | pair_bit(0, 3) | pair_bit(0, 4) | pair_bit(0, 5);
+}
+
+// Quiet-step test of the tiled kernel.  The gripper trajectory of this step (computed without
+// cubes) stayed inside [lo, hi] per axis with finger opening <= qmax.  If every cube is separated
+// from that swept finger volume by more than the contact margin along world x, y or z -- the same
+// three axes (k = 0, 1 and z) collide_finger_block tests -- no substep can report a finger contact,
+// so the cubes (already on a fixed point) are untouched by this step.  kQuietEps absorbs rounding.
+constexpr float kQuietEps = 1e-5f;
+__device__ __forceinline__ bool cube_out_of_reach(float bx, float by, float bz, float c, float s,
+                                                  const float lo[3], const float hi[3], float qmax) {
+    const float RB = kHB * fabsf(c) + kHB * fabsf(s);
+    const float pad = kMargin + kQuietEps;
+    const float sepx = fmaxf(bx - hi[0], lo[0] - bx);
+    const float sepy = fmaxf(by - hi[1], lo[1] - by);
+    const float sepz = fmaxf(bz - (hi[2] + kFZOff), (lo[2] + kFZOff) - bz);
+    return sepx >= (kFX + RB) + pad || sepy >= ((kFY0 + qmax) + kFY + RB) + pad || sepz >= (kFZ + kHB) + pad;
 }
 
 // ---------------------------------------------------------------- RNG replay
@@ -657,6 +747,7 @@ __device__ __forceinline__ void env_reset(Env<Cfg<ID>::NB>& e, const Ranges& rg)
     e.succ = 0;
     e.t = 0;
     e.episode = ep + 1;
+    e.priv = 0;
 }
 
 // -(d != c).astype(float32): -1.0 or -0.0 (appendix A7).  Stored as an integer bit pattern: nvcc
@@ -757,25 +848,26 @@ __device__ __forceinline__ void env_write_goal(Store&& put) {
         }
 }
 
-// RobotEnv.step (robot_env.py:57-69) for one env; returns true when the reward is -1 (false: -0.0),
-// updates latch and t.
-template <int ID>
-__device__ __forceinline__ bool env_step(Env<Cfg<ID>::NB>& e, float a0, float a1, float a2, float a3, int& invalid) {
-    using C = Cfg<ID>;
-    float a[4] = {a0, a1, a2, a3};
+// np.clip(action, -1, 1) (robot_env.py:58); NaN components are zeroed and counted, not raised
+__device__ __forceinline__ void clip_action(float a[4], int& invalid) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         float x = a[k];
         if (!(x == x)) { x = 0.0f; invalid += 1; }
-        a[k] = x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x);  // np.clip, robot_env.py:58
+        a[k] = x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x);
     }
-    sim_step<C::NB, C::BG>(e, a);
-    // _step_callback fetch_env.py:148-167: 1 -> 0 downgrade, then contacts -> 1
-    e.touch_now = e.contacts;
-    e.touch_ever |= e.contacts;
-    const bool fail = env_reward_fail<ID>(e.touch_now, e.touch_ever);
-    if (!fail) e.succ = 1;  // _is_success latch (r == 0), fetch_env.py:275-281
-    e.t += 1;
+}
+
+// what RobotEnv.step does after sim.step(): _step_callback (fetch_env.py:148-167: 1 -> 0 downgrade,
+// then contacts -> 1), reward (fetch_env.py:135-143), _is_success latch (fetch_env.py:275-281), TimeLimit count.
+// Returns true when the reward is -1 (false: -0.0).
+template <int ID>
+__device__ __forceinline__ bool env_post_step(uint32_t contacts, uint32_t& touch_now, uint32_t& touch_ever, int& succ, int& t) {
+    touch_now = contacts;
+    touch_ever |= contacts;
+    const bool fail = env_reward_fail<ID>(touch_now, touch_ever);
+    if (!fail) succ = 1;
+    t += 1;
     return fail;
 }
 

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -16,7 +17,7 @@
 namespace bp {
 
 // ---------------------------------------------------------------- state <-> registers
-template <int NB> __host__ __device__ constexpr int num_fields() { return 17 + 9 * NB; }
+template <int NB> __host__ __device__ constexpr int num_fields() { return 18 + 9 * NB; }
 
 template <int NB>
 __device__ __forceinline__ void load_env(const uint32_t* __restrict__ st, int64_t B, int64_t i, Env<NB>& e) {
@@ -37,6 +38,7 @@ __device__ __forceinline__ void load_env(const uint32_t* __restrict__ st, int64_
     e.touch_now = touch & 0xffffu; e.touch_ever = touch >> 16;
     uint32_t flags = ldu();
     e.t = (int)(flags & 0xffu); e.succ = (int)((flags >> 8) & 1u); e.nb = (int)((flags >> 9) & 7u);
+    e.priv = ldu();
     e.episode = ldu(); e.draws0 = ldu(); e.draws1 = ldu();
     e.key0 = ldu(); e.key1 = ldu();
     e.contacts = 0;
@@ -59,6 +61,7 @@ __device__ __forceinline__ void store_env(uint32_t* __restrict__ st, int64_t B, 
     }
     stu(e.touch_now | (e.touch_ever << 16));
     stu((uint32_t)e.t | ((uint32_t)e.succ << 8) | ((uint32_t)e.nb << 9));
+    stu(e.priv);
     stu(e.episode); stu(e.draws0); stu(e.draws1);
     stu(e.key0); stu(e.key1);
 }
@@ -74,7 +77,7 @@ __global__ void init_kernel(uint32_t* st, int64_t B) {
     e.nb = C::NB;
     sim_init<C::NB>(e, ID == 2);
     e.touch_now = 0; e.touch_ever = 0;  // achieved_goal = -1 everywhere, fetch_env.py:78
-    e.t = 0; e.succ = 0; e.episode = 0; e.draws0 = 0; e.draws1 = 0; e.key0 = 0; e.key1 = 0;
+    e.t = 0; e.succ = 0; e.episode = 0; e.draws0 = 0; e.draws1 = 0; e.key0 = 0; e.key1 = 0; e.priv = 0;
     store_env<C::NB>(st, B, i, e);
 }
 
@@ -131,6 +134,7 @@ __global__ void set_test_kernel(uint32_t* st, int64_t B, Ranges rg, float* obs, 
     if (g) write_row_goal<ID>(g + i * C::DIMG);
     if (!C::VAR) {
         randomize_objects<ID>(e, e.episode - 1u, true, rg);
+        e.priv = 0;
         store_env<C::NB>(st, B, i, e);
     }
 }
@@ -160,29 +164,62 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// v0: one thread per env, K fused steps, state in registers, direct stores.
+// Env<NB> (registers) <-> Grip + private cube column
+template <int NB, int STRIDE>
+__device__ __forceinline__ void env_to_col(const Env<NB>& e, Grip& g, const Col<NB, STRIDE> col) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { g.g[d] = e.g[d]; g.gv[d] = e.gv[d]; }
+    g.q[0] = e.q[0]; g.q[1] = e.q[1]; g.qv[0] = e.qv[0]; g.qv[1] = e.qv[1];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) col.store(b, Blk{e.px[b], e.py[b], e.pz[b], e.c[b], e.s[b], e.vx[b], e.vy[b], e.vz[b], e.w[b]});
+}
+template <int NB, int STRIDE>
+__device__ __forceinline__ void col_to_env(Env<NB>& e, const Grip& g, const Col<NB, STRIDE> col) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { e.g[d] = g.g[d]; e.gv[d] = g.gv[d]; }
+    e.q[0] = g.q[0]; e.q[1] = g.q[1]; e.qv[0] = g.qv[0]; e.qv[1] = g.qv[1];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const Blk k = col.load(b);
+        e.px[b] = k.x; e.py[b] = k.y; e.pz[b] = k.z; e.c[b] = k.c; e.s[b] = k.s; e.vx[b] = k.vx; e.vy[b] = k.vy; e.vz[b] = k.vz; e.w[b] = k.w;
+    }
+}
+
+// Reference kernel: one thread per env, every step runs the full physics (no quiet path),
+// direct stores.  Selected with BP_STEP_KERNEL=simple; the tests use it to cross-check the
+// tiled kernel's quiet path bit for bit.
 template <int ID>
 __global__ void __launch_bounds__(128) step_kernel_simple(uint32_t* st, StepArgs p) {
     using C = Cfg<ID>;
+    constexpr int NB = C::NB;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const Col<NB, 128> col{reinterpret_cast<float*>(smem) + threadIdx.x};
     int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index inside this launch
     const bool live = li < p.B;
     float n_ep = 0.f, n_su = 0.f, n_st = 0.f, n_inv = 0.f, r_sum = 0.f;
     if (live) {
         const int64_t i = p.env0 + li;
-        Env<C::NB> e;
-        load_env<C::NB>(st, p.stateB, i, e);
+        Env<NB> e;
+        load_env<NB>(st, p.stateB, i, e);
         for (int k = 0; k < p.K; ++k) {
             const int64_t row = (int64_t)k * p.B + li;
-            float4 a;
+            float4 a4;
             if (p.actions) {
-                a = reinterpret_cast<const float4*>(p.actions)[row];
+                a4 = reinterpret_cast<const float4*>(p.actions)[row];
             } else {
                 U4 w = philox4x32((uint32_t)e.t, e.episode - 1u, 2u, 0u, e.key0, e.key1);
-                a = make_float4(2.0f * u01(w.x) - 1.0f, 2.0f * u01(w.y) - 1.0f, 2.0f * u01(w.z) - 1.0f, 2.0f * u01(w.w) - 1.0f);
+                a4 = make_float4(2.0f * u01(w.x) - 1.0f, 2.0f * u01(w.y) - 1.0f, 2.0f * u01(w.z) - 1.0f, 2.0f * u01(w.w) - 1.0f);
             }
-            if (p.actions_out) reinterpret_cast<float4*>(p.actions_out)[row] = a;
+            if (p.actions_out) reinterpret_cast<float4*>(p.actions_out)[row] = a4;
             int inv = 0;
-            const bool fail = env_step<ID>(e, a.x, a.y, a.z, a.w, inv);
+            float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            clip_action(a, inv);
+            Grip g;
+            env_to_col<NB, 128>(e, g, col);
+            sim_step_col<NB, 128, C::BG>(g, a, col, e.nb, e.contacts);
+            col_to_env<NB, 128>(e, g, col);
+            e.priv = 0;
+            const bool fail = env_post_step<ID>(e.contacts, e.touch_now, e.touch_ever, e.succ, e.t);
             if (p.obs) write_row_obs<ID>(e, p.obs + row * C::DIMO);
             if (p.ag) write_row_ag<ID>(e, p.ag + row * C::DIMG);
             if (p.reward) store_reward(p.reward + row, fail);
@@ -199,10 +236,332 @@ __global__ void __launch_bounds__(128) step_kernel_simple(uint32_t* st, StepArgs
                 }
             }
         }
-        store_env<C::NB>(st, p.stateB, i, e);
+        store_env<NB>(st, p.stateB, i, e);
     }
     n_ep = warp_sum(n_ep); n_su = warp_sum(n_su); n_st = warp_sum(n_st); n_inv = warp_sum(n_inv); r_sum = warp_sum(r_sum);
     if ((threadIdx.x & 31) == 0 && p.stats) {
+        if (n_ep != 0.f) atomicAdd(p.stats + BP_STAT_EPISODES, (double)n_ep);
+        if (n_su != 0.f) atomicAdd(p.stats + BP_STAT_SUCCESSES, (double)n_su);
+        if (n_st != 0.f) atomicAdd(p.stats + BP_STAT_STEPS, (double)n_st);
+        if (n_inv != 0.f) atomicAdd(p.stats + BP_STAT_INVALID, (double)n_inv);
+        if (r_sum != 0.f) atomicAdd(p.stats + BP_STAT_REWARD_SUM, (double)r_sum);
+    }
+}
+
+// ---------------------------------------------------------------- tiled step kernel
+// One CTA of 128 threads owns a tile of 256 envs for all K fused steps.  Cube state lives in shared
+// memory (SoA), the gripper state of each env in the registers of its owner thread (2 envs/thread).
+// Every step has three phases:
+//   A  owners: clip the action, integrate the gripper alone (20 substeps) while tracking the swept
+//      finger volume.  If the cubes sit on an exact fixed point and the swept volume cannot reach
+//      any cube, the step is "quiet": its result is the gripper trajectory just computed and the
+//      stored cube-contact set.  Otherwise the env id goes to the tile's active list.
+//   B  workers: the active list is compacted, so full 32-lane warps run the complete BlockPhys step
+//      (gripper + cubes + contacts) for exactly the envs that need it.
+//   C  owners: touch matrix / reward / latch / TimeLimit, observation rows staged through shared
+//      memory and written with fully coalesced stores, auto-reset.
+// The quiet path is result-neutral (see cube_out_of_reach), so outputs are bit-identical to the
+// simple kernel and to the oracle.
+template <int ID>
+struct Tile {
+    using C = Cfg<ID>;
+    static constexpr int NB = C::NB;
+    static constexpr int TILE = 256, THREADS = 128, EPT = 2, NW = THREADS / 32;
+    static constexpr int OSTR = (C::DIMO % 2 == 0) ? C::DIMO + 1 : C::DIMO;  // odd row stride: conflict-free scalar STS
+    static constexpr int GSTR = (C::DIMG % 2 == 0) ? C::DIMG + 1 : C::DIMG;
+    static constexpr int STAGE = 32 * OSTR;
+    static constexpr int W_COL = Col<NB, THREADS>::kFields * THREADS;  // private worker columns, aliased with the stage
+    static constexpr int W_STAGE = (NW * STAGE > W_COL) ? NW * STAGE : W_COL;
+    static constexpr int W_BLK = 9 * NB * TILE, W_GRIP = 10 * TILE, W_ACT = 4 * TILE, W_CTC = TILE, W_LIST = TILE / 2;
+    static constexpr size_t SMEM = sizeof(uint32_t) * (size_t)(W_BLK + W_GRIP + W_ACT + W_CTC + W_STAGE + W_LIST + 4);
+};
+
+// flush `nv` staged rows (row stride SSTR in shared memory) of W floats each to a contiguous global range
+template <int W, int SSTR>
+__device__ __forceinline__ void flush_rows(const float* stage, float* __restrict__ dst, int nv, int lane) {
+    const int total = nv * W;
+    for (int idx = lane; idx < total; idx += 32) {
+        const int row = idx / W, col = idx - row * W;
+        dst[idx] = stage[row * SSTR + col];
+    }
+}
+
+// RobotEnv.reset for one env of a tile: kept out of line (it is rare and large: Philox, log, sincos)
+template <int ID>
+__device__ __noinline__ void reset_in_tile(uint32_t* __restrict__ st, const StepArgs& p, int64_t gi, int64_t li, Grip& gr,
+                                           float* blk_col /* s_blk + le, stride TILE */, int& nb, uint32_t& touch_now, uint32_t& touch_ever) {
+    using C = Cfg<ID>;
+    constexpr int NB = C::NB;
+    constexpr int NF = num_fields<NB>();
+    constexpr int TILE = 256;
+    Env<NB> e;
+    e.nb = nb;
+    e.touch_now = touch_now; e.touch_ever = touch_ever;
+    e.episode = st[(int64_t)(NF - 5) * p.stateB + gi];
+    e.key0 = st[(int64_t)(NF - 2) * p.stateB + gi]; e.key1 = st[(int64_t)(NF - 1) * p.stateB + gi];
+    env_reset<ID>(e, p.rg);
+    st[(int64_t)(NF - 5) * p.stateB + gi] = e.episode;
+    st[(int64_t)(NF - 4) * p.stateB + gi] = e.draws0;
+    st[(int64_t)(NF - 3) * p.stateB + gi] = e.draws1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { gr.g[d] = e.g[d]; gr.gv[d] = e.gv[d]; }
+    gr.q[0] = e.q[0]; gr.q[1] = e.q[1]; gr.qv[0] = e.qv[0]; gr.qv[1] = e.qv[1];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        float* bb = blk_col + (9 * b) * TILE;
+        bb[0] = e.px[b]; bb[TILE] = e.py[b]; bb[2 * TILE] = e.pz[b]; bb[3 * TILE] = e.c[b]; bb[4 * TILE] = e.s[b];
+        bb[5 * TILE] = e.vx[b]; bb[6 * TILE] = e.vy[b]; bb[7 * TILE] = e.vz[b]; bb[8 * TILE] = e.w[b];
+    }
+    nb = e.nb; touch_now = e.touch_now; touch_ever = e.touch_ever;
+    if (p.reset_obs) write_row_obs<ID>(e, p.reset_obs + li * C::DIMO);
+    if (p.reset_ag) write_row_ag<ID>(e, p.reset_ag + li * C::DIMG);
+}
+
+template <int ID>
+__global__ void __launch_bounds__(128, 4) step_kernel_tiled(uint32_t* __restrict__ st, StepArgs p) {
+    using T = Tile<ID>;
+    using C = Cfg<ID>;
+    constexpr int NB = C::NB, TILE = T::TILE, EPT = T::EPT, NW = T::NW;
+    constexpr int NF = num_fields<NB>();
+    extern __shared__ __align__(16) uint32_t smem[];
+    float* s_blk = reinterpret_cast<float*>(smem);                  // [9*NB][TILE]
+    float* s_grip = s_blk + T::W_BLK;                               // [10][TILE]  gripper state exchange for active envs
+    float* s_act = s_grip + T::W_GRIP;                              // [4][TILE]   clipped action of active envs
+    uint32_t* s_ctc = reinterpret_cast<uint32_t*>(s_act + T::W_ACT);  // [TILE] in: nb; out: contacts | static << 31
+    float* s_stage = reinterpret_cast<float*>(s_ctc + T::W_CTC);    // [NW][STAGE]
+    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_stage + T::W_STAGE);  // [TILE]
+    int* s_nact = reinterpret_cast<int*>(s_list + TILE);            // [2] double-buffered active counter
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile0 = (int64_t)blockIdx.x * TILE;  // launch-local index of the tile's env 0
+    float* my_stage = s_stage + warp * T::STAGE;
+    const Col<NB, T::THREADS> wcol{s_stage + tid};  // worker column (phase B only; the stage is idle then)
+
+    // ---- owner state, 2 envs per thread: slot j owns local env le = j*128 + tid
+    Grip gr[EPT];
+    uint32_t touch_now[EPT], touch_ever[EPT], priv[EPT];
+    int tt[EPT], succ[EPT], nb[EPT];
+    bool live[EPT];
+    float n_ep = 0.f, n_su = 0.f, n_st = 0.f, n_inv = 0.f, r_sum = 0.f, n_act = 0.f;
+
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        const int le = j * T::THREADS + tid;
+        const int64_t li = tile0 + le;
+        live[j] = li < p.B;
+        const int64_t gi = p.env0 + (live[j] ? li : 0);
+        const uint32_t* q = st + gi;
+        int f = 0;
+        auto ldf = [&]() { float v = __uint_as_float(q[(int64_t)f * p.stateB]); ++f; return v; };
+        auto ldu = [&]() { uint32_t v = q[(int64_t)f * p.stateB]; ++f; return v; };
+        gr[j].g[0] = ldf(); gr[j].g[1] = ldf(); gr[j].g[2] = ldf();
+        gr[j].gv[0] = ldf(); gr[j].gv[1] = ldf(); gr[j].gv[2] = ldf();
+        gr[j].q[0] = ldf(); gr[j].q[1] = ldf(); gr[j].qv[0] = ldf(); gr[j].qv[1] = ldf();
+#pragma unroll
+        for (int w = 0; w < 9 * NB; ++w) s_blk[w * TILE + le] = ldf();
+        const uint32_t touch = ldu();
+        touch_now[j] = touch & 0xffffu; touch_ever[j] = touch >> 16;
+        const uint32_t flags = ldu();
+        tt[j] = (int)(flags & 0xffu); succ[j] = (int)((flags >> 8) & 1u); nb[j] = (int)((flags >> 9) & 7u);
+        priv[j] = ldu();
+    }
+    if (tid < 2) s_nact[tid] = 0;
+    __syncthreads();
+
+    for (int k = 0; k < p.K; ++k) {
+        float act[EPT][4];
+        uint32_t ctc[EPT];
+        bool active[EPT];
+        int inv = 0;
+        int* nact = s_nact + (k & 1);
+        // ------------------------------------------------------------ phase A
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int le = j * T::THREADS + tid;
+            const int64_t li = tile0 + le;
+            active[j] = false;
+            ctc[j] = 0;
+            if (!live[j]) continue;
+            const int64_t row = (int64_t)k * p.B + li;
+            float4 a4;
+            if (p.actions) {
+                a4 = __ldg(reinterpret_cast<const float4*>(p.actions) + row);
+            } else {
+                const int64_t gi = p.env0 + li;
+                const uint32_t ep = st[(int64_t)(NF - 5) * p.stateB + gi];
+                const uint32_t k0 = st[(int64_t)(NF - 2) * p.stateB + gi], k1 = st[(int64_t)(NF - 1) * p.stateB + gi];
+                U4 w = philox4x32((uint32_t)tt[j], ep - 1u, 2u, 0u, k0, k1);
+                a4 = make_float4(2.0f * u01(w.x) - 1.0f, 2.0f * u01(w.y) - 1.0f, 2.0f * u01(w.z) - 1.0f, 2.0f * u01(w.w) - 1.0f);
+            }
+            if (p.actions_out) reinterpret_cast<float4*>(p.actions_out)[row] = a4;
+            act[j][0] = a4.x; act[j][1] = a4.y; act[j][2] = a4.z; act[j][3] = a4.w;
+            clip_action(act[j], inv);
+            bool quiet = (priv[j] >> 31) != 0;
+            Grip g2 = gr[j];
+            if (quiet) {
+                float m[3], ctrl[2];
+                action_targets<C::BG>(g2, act[j], m, ctrl);
+                float lo[3] = {g2.g[0], g2.g[1], g2.g[2]}, hi[3] = {g2.g[0], g2.g[1], g2.g[2]};
+                float qmax = fmaxf(g2.q[0], g2.q[1]);
+#pragma unroll 4
+                for (int sub = 0; sub < kNSub; ++sub) {
+                    GripSub gs;
+                    substep_gripper<C::BG>(g2, gs, m, ctrl);
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { lo[d] = fminf(lo[d], g2.g[d]); hi[d] = fmaxf(hi[d], g2.g[d]); }
+                    if (!C::BG) qmax = fmaxf(qmax, fmaxf(g2.q[0], g2.q[1]));
+                }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    if (b < nb[j]) {
+                        const float* bb = s_blk + (9 * b) * TILE + le;
+                        quiet = quiet && cube_out_of_reach(bb[0], bb[TILE], bb[2 * TILE], bb[3 * TILE], bb[4 * TILE], lo, hi, qmax);
+                    }
+                }
+            }
+            if (quiet) {
+                gr[j] = g2;
+                ctc[j] = priv[j] & 0x7fffu;
+                if (over_table(g2.g[0], g2.g[1]) && g2.g[2] - kGZMin < kMargin) ctc[j] |= pair_bit(0, 1);
+            } else {
+                active[j] = true;
+                n_act += 1.f;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) { s_grip[d * TILE + le] = gr[j].g[d]; s_grip[(3 + d) * TILE + le] = gr[j].gv[d]; }
+                s_grip[6 * TILE + le] = gr[j].q[0]; s_grip[7 * TILE + le] = gr[j].q[1];
+                s_grip[8 * TILE + le] = gr[j].qv[0]; s_grip[9 * TILE + le] = gr[j].qv[1];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) s_act[d * TILE + le] = act[j][d];
+                s_ctc[le] = (uint32_t)nb[j];
+                const int slot = atomicAdd(nact, 1);
+                s_list[slot] = (uint16_t)le;
+            }
+        }
+        __syncthreads();
+        // ------------------------------------------------------------ phase B
+        {
+            const int n = *nact;
+            for (int base = warp * 32; base < n; base += NW * 32) {
+                const int i = base + lane;
+                if (i < n) {
+                    const int le = s_list[i];
+                    Grip g;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { g.g[d] = s_grip[d * TILE + le]; g.gv[d] = s_grip[(3 + d) * TILE + le]; }
+                    g.q[0] = s_grip[6 * TILE + le]; g.q[1] = s_grip[7 * TILE + le];
+                    g.qv[0] = s_grip[8 * TILE + le]; g.qv[1] = s_grip[9 * TILE + le];
+#pragma unroll
+                    for (int w = 0; w < 9 * NB; ++w) wcol.p[w * T::THREADS] = s_blk[w * TILE + le];
+                    const int nbv = (int)s_ctc[le];
+                    float a[4] = {s_act[le], s_act[TILE + le], s_act[2 * TILE + le], s_act[3 * TILE + le]};
+                    uint32_t contacts = 0;
+                    const bool is_static = sim_step_col<NB, T::THREADS, C::BG>(g, a, wcol, nbv, contacts);
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { s_grip[d * TILE + le] = g.g[d]; s_grip[(3 + d) * TILE + le] = g.gv[d]; }
+                    s_grip[6 * TILE + le] = g.q[0]; s_grip[7 * TILE + le] = g.q[1];
+                    s_grip[8 * TILE + le] = g.qv[0]; s_grip[9 * TILE + le] = g.qv[1];
+#pragma unroll
+                    for (int w = 0; w < 9 * NB; ++w) s_blk[w * TILE + le] = wcol.p[w * T::THREADS];
+                    s_ctc[le] = contacts | (is_static ? 0x80000000u : 0u);
+                }
+            }
+            if (tid == 0) s_nact[(k + 1) & 1] = 0;
+        }
+        __syncthreads();
+        // ------------------------------------------------------------ phase C
+#pragma unroll
+        for (int j = 0; j < EPT; ++j) {
+            const int le = j * T::THREADS + tid;
+            const int64_t li = tile0 + le;
+            const int64_t rg0 = tile0 + j * T::THREADS + warp * 32;  // launch-local index of this row group's env 0
+            int nv = (int)((p.B - rg0) < 32 ? (p.B - rg0) : 32);
+            if (nv < 0) nv = 0;
+            const int64_t row = (int64_t)k * p.B + li;
+            bool fail = false, done = false;
+            if (live[j]) {
+                if (active[j]) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { gr[j].g[d] = s_grip[d * TILE + le]; gr[j].gv[d] = s_grip[(3 + d) * TILE + le]; }
+                    gr[j].q[0] = s_grip[6 * TILE + le]; gr[j].q[1] = s_grip[7 * TILE + le];
+                    gr[j].qv[0] = s_grip[8 * TILE + le]; gr[j].qv[1] = s_grip[9 * TILE + le];
+                    const uint32_t res = s_ctc[le];
+                    ctc[j] = res & 0x7fffu;
+                    priv[j] = (res & 0x80000000u) | (ctc[j] & ~gripper_pair_mask());
+                }
+                fail = env_post_step<ID>(ctc[j], touch_now[j], touch_ever[j], succ[j], tt[j]);
+                done = tt[j] >= kT;
+                n_st += 1.f; r_sum += fail ? -1.f : 0.f;
+                if (p.reward) store_reward(p.reward + row, fail);
+                if (p.success) p.success[row] = (float)succ[j];
+                if (p.done) p.done[row] = done ? 1 : 0;
+            }
+            // observation rows: registers + shared cube state -> stage -> coalesced global stores
+            if (p.obs) {
+                if (live[j]) {
+                    Env<NB> e;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) { e.g[d] = gr[j].g[d]; e.gv[d] = gr[j].gv[d]; }
+                    e.q[0] = gr[j].q[0]; e.q[1] = gr[j].q[1]; e.qv[0] = gr[j].qv[0]; e.qv[1] = gr[j].qv[1];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const float* bb = s_blk + (9 * b) * TILE + le;
+                        e.px[b] = bb[0]; e.py[b] = bb[TILE]; e.pz[b] = bb[2 * TILE]; e.c[b] = bb[3 * TILE]; e.s[b] = bb[4 * TILE];
+                        e.vx[b] = bb[5 * TILE]; e.vy[b] = bb[6 * TILE]; e.vz[b] = bb[7 * TILE]; e.w[b] = bb[8 * TILE];
+                    }
+                    e.nb = nb[j];
+                    float* srow = my_stage + lane * T::OSTR;
+                    env_write_obs<ID>(e, [&](int c, float v) { srow[c] = v; });
+                }
+                __syncwarp();
+                flush_rows<C::DIMO, T::OSTR>(my_stage, p.obs + ((int64_t)k * p.B + rg0) * C::DIMO, nv, lane);
+                __syncwarp();
+            }
+            if (p.ag) {
+                if (live[j]) {
+                    float* srow = my_stage + lane * T::GSTR;
+                    env_write_ag<ID>(touch_now[j], touch_ever[j], [&](int c, float v) { srow[c] = v; });
+                }
+                __syncwarp();
+                flush_rows<C::DIMG, T::GSTR>(my_stage, p.ag + ((int64_t)k * p.B + rg0) * C::DIMG, nv, lane);
+                __syncwarp();
+            }
+            if (live[j] && done) {
+                n_ep += 1.f; n_su += (float)succ[j];
+                if (p.auto_reset) {
+                    // RobotEnv.reset inside the kernel (rare: once per 50 steps and env)
+                    reset_in_tile<ID>(st, p, p.env0 + li, li, gr[j], s_blk + le, nb[j], touch_now[j], touch_ever[j]);
+                    succ[j] = 0; tt[j] = 0; priv[j] = 0;
+                }
+            }
+        }
+        n_inv += (float)inv;
+        // phase C of this step and phase A of the next touch only the owner's own columns of s_blk /
+        // s_grip / s_act, so no barrier is needed here; the two barriers above order the worker accesses.
+    }
+
+    // ---- write the state back
+#pragma unroll
+    for (int j = 0; j < EPT; ++j) {
+        if (!live[j]) continue;
+        const int le = j * T::THREADS + tid;
+        const int64_t gi = p.env0 + tile0 + le;
+        uint32_t* q = st + gi;
+        int f = 0;
+        auto stf = [&](float v) { q[(int64_t)f * p.stateB] = __float_as_uint(v); ++f; };
+        auto stu = [&](uint32_t v) { q[(int64_t)f * p.stateB] = v; ++f; };
+        stf(gr[j].g[0]); stf(gr[j].g[1]); stf(gr[j].g[2]);
+        stf(gr[j].gv[0]); stf(gr[j].gv[1]); stf(gr[j].gv[2]);
+        stf(gr[j].q[0]); stf(gr[j].q[1]); stf(gr[j].qv[0]); stf(gr[j].qv[1]);
+#pragma unroll
+        for (int w = 0; w < 9 * NB; ++w) stf(s_blk[w * TILE + le]);
+        stu(touch_now[j] | (touch_ever[j] << 16));
+        stu((uint32_t)tt[j] | ((uint32_t)succ[j] << 8) | ((uint32_t)nb[j] << 9));
+        stu(priv[j]);
+    }
+    n_ep = warp_sum(n_ep); n_su = warp_sum(n_su); n_st = warp_sum(n_st); n_inv = warp_sum(n_inv); r_sum = warp_sum(r_sum);
+    n_act = warp_sum(n_act);
+    if (lane == 0 && p.stats) {
+        if (n_act != 0.f) atomicAdd(p.stats + BP_STAT_WORKER_STEPS, (double)n_act);
         if (n_ep != 0.f) atomicAdd(p.stats + BP_STAT_EPISODES, (double)n_ep);
         if (n_su != 0.f) atomicAdd(p.stats + BP_STAT_SUCCESSES, (double)n_su);
         if (n_st != 0.f) atomicAdd(p.stats + BP_STAT_STEPS, (double)n_st);
@@ -274,6 +633,7 @@ __global__ void set_state_kernel(uint32_t* st, int64_t B, const bp_env_state* in
     e.t = s.t;
     e.episode = s.episode;
     e.draws0 = s.draws[0]; e.draws1 = s.draws[1];
+    e.priv = 0;
     store_env<C::NB>(st, B, i, e);
 }
 
@@ -440,7 +800,7 @@ int bp_create(int env_id, int64_t num_envs, int device, uint64_t env_index_offse
     CU(cudaSetDevice(device));
     bp_handle* h = new bp_handle();
     h->env_id = env_id; h->device = device; h->B = num_envs; h->env_offset = env_index_offset;
-    h->nf = 17 + 9 * kNB[env_id];
+    h->nf = 18 + 9 * kNB[env_id];
     switch (env_id) {  // fetch_env.py:340-348, 404-415, 561-563 on top of tasks.py obj_range=0.15
         case BP_BLOCKS_TOUCH: h->max_obj_range = h->obj_range; h->obj_range_step = 0; h->has_step = true; h->has_curriculum = true; break;
         case BP_BLOCKS_TOUCH_CURRICULUM:
@@ -507,10 +867,28 @@ int bp_reset(bp_handle* h, const uint8_t* d_mask, float* d_obs, float* d_ag, flo
     return BP_OK;
 }
 
+static bool use_simple_kernel() {
+    static const bool v = [] { const char* e = getenv("BP_STEP_KERNEL"); return e && strcmp(e, "simple") == 0; }();
+    return v;
+}
+
 static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
     int rc = dispatch(h->env_id, [&](auto id) {
-        step_kernel_simple<decltype(id)::value><<<nblk(a.B, 128), 128, 0, s>>>(h->d_state, a);
-        return BP_OK;
+        constexpr int ID = decltype(id)::value;
+        if (use_simple_kernel()) {
+            constexpr size_t kSmem = sizeof(float) * Col<Cfg<ID>::NB, 128>::kFields * 128;
+            step_kernel_simple<ID><<<nblk(a.B, 128), 128, kSmem, s>>>(h->d_state, a);
+        } else {
+            using T = Tile<ID>;
+            static bool attr_set[BP_NUM_ENV_IDS] = {};
+            if (!attr_set[ID]) {
+                cudaError_t e = cudaFuncSetAttribute(step_kernel_tiled<ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+                if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+                attr_set[ID] = true;
+            }
+            step_kernel_tiled<ID><<<nblk(a.B, T::TILE), T::THREADS, T::SMEM, s>>>(h->d_state, a);
+        }
+        return (int)BP_OK;
     });
     if (rc != BP_OK) return rc;
     CU(cudaGetLastError());

@@ -60,7 +60,8 @@ enum {
     BP_STAT_SUCCESSES = 1,  /* of those, is_success at the last step (rollout.py:163-167) */
     BP_STAT_STEPS = 2,
     BP_STAT_INVALID = 3,    /* non-finite action components (replaces the NaN restart, rollout.py:139-142) */
-    BP_STAT_REWARD_SUM = 4
+    BP_STAT_REWARD_SUM = 4,
+    BP_STAT_WORKER_STEPS = 5 /* diagnostic: env-steps that took the full-physics worker path of the tiled kernel */
 };
 
 /* Canonical per-env state record used by bp_get_state / bp_set_state (the
