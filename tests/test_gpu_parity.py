@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the
 same seeded inputs.  Bar: bit-exact for integer state (touch matrix, latch, counters, Philox
 draw counters) AND bit-identical fp32 for every float (BlockPhys v1 fixes the op order)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -256,3 +258,26 @@ def test_gym_single_env_surface():
         assert info["is_success"] == bool(s2[0])
         assert done == (t == 49)
         assert env.compute_reward(o["achieved_goal"], o["desired_goal"], info) == r
+
+
+def test_simple_and_tiled_kernels_agree():
+    """The tiled kernel's quiet path must be result-neutral: BP_STEP_KERNEL=simple runs the full physics
+    for every env-step; both must leave byte-identical state and outputs (checked via hashes)."""
+    import hashlib
+    import subprocess
+    import sys
+    code = (
+        "import hashlib, torch, blockpuzzle_gym_b200 as bpg\n"
+        "h = hashlib.sha256()\n"
+        "for name in ('BlocksTouch-v0', 'ToppleTower-v0', 'BlocksTouchVariation-v0', 'GripperTouch-v0'):\n"
+        "    env = bpg.make_vec(name, 1000, device=0, seed=13); env.reset()\n"
+        "    out = env.step_fused(None, K=130, auto_reset=True)\n"
+        "    for k in ('observation', 'achieved_goal', 'reward', 'is_success'): h.update(out[k].cpu().numpy().tobytes())\n"
+        "    h.update(env.get_state().tobytes())\n"
+        "print(h.hexdigest())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for mode in ("tiled", "simple"):
+        env = dict(os.environ, BP_STEP_KERNEL=mode, PYTHONPATH=root)
+        outs.append(subprocess.check_output([sys.executable, "-c", code], env=env, cwd=root).decode().strip().splitlines()[-1])
+    assert outs[0] == outs[1]
