@@ -186,10 +186,13 @@ def run_ours(args):
     out = {}
     stats = env.stats_tensor()
 
+    gstats = torch.zeros_like(stats)
+
     def launch():
         env.step_fused(actions, auto_reset=True, out=out)
+        gstats.copy_(stats)
         if world > 1:
-            dist.all_reduce(stats)  # replaces mpi_moments (train.py:21-26); one tiny all-reduce per launch
+            dist.all_reduce(gstats)  # replaces mpi_moments (train.py:21-26); one tiny all-reduce per launch
 
     def sync():
         if world > 1:
@@ -217,7 +220,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    st = env.stats()
+    from blockpuzzle_gym_b200.dist import stats_dict
+    st = stats_dict(gstats)  # global (all-rank) statistics of the timed launches
 
     # ---- e2e: the same metric through the C-ABI with HOST buffers (pinned), copies inside the timed region
     Ke, Be = args.e2e_fused, B

@@ -730,6 +730,30 @@ __device__ __forceinline__ void randomize_objects(Env<Cfg<ID>::NB>& e, uint32_t 
     }
 }
 
+// Kernel-private flags right after a spawn.  Spawned cubes rest on the table top (or form the
+// ToppleTower stack) with zero velocity and yaw: an exact fixed point of substep_cubes as long as no
+// two cubes are within contact range, which is verified here (yaw = 0: the SAT reduces to |dx|, |dy|).
+// Returns bit 31 (cubes static) | the cube-only contact pairs such a substep reports, or 0 when unsure.
+template <int ID>
+__device__ __forceinline__ uint32_t spawn_priv(const Env<Cfg<ID>::NB>& e) {
+    constexpr int NB = Cfg<ID>::NB;
+    if (ID == 2)  // tower: table-cube0 and the three stacked pairs (identical xy)
+        return 0x80000000u | pair_bit(1, 2) | pair_bit(2, 3) | pair_bit(3, 4) | pair_bit(4, 5);
+    bool ok = true;
+    uint32_t contacts = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (i < e.nb) {
+            ok = ok && over_table(e.px[i], e.py[i]);
+            contacts |= pair_bit(1, 2) << i;
+#pragma unroll
+            for (int j = i + 1; j < NB; ++j)
+                if (j < e.nb) ok = ok && (fabsf(e.px[j] - e.px[i]) > 0.0511f || fabsf(e.py[j] - e.py[i]) > 0.0511f);
+        }
+    }
+    return ok ? (0x80000000u | contacts) : 0u;
+}
+
 // RobotEnv.reset (robot_env.py:71-82) + _reset_sim (fetch_env.py:247-255, Variation :646-679) + TimeLimit reset
 template <int ID>
 __device__ __forceinline__ void env_reset(Env<Cfg<ID>::NB>& e, const Ranges& rg) {
@@ -747,7 +771,7 @@ __device__ __forceinline__ void env_reset(Env<Cfg<ID>::NB>& e, const Ranges& rg)
     e.succ = 0;
     e.t = 0;
     e.episode = ep + 1;
-    e.priv = 0;
+    e.priv = spawn_priv<ID>(e);
 }
 
 // -(d != c).astype(float32): -1.0 or -0.0 (appendix A7).  Stored as an integer bit pattern: nvcc

@@ -267,8 +267,10 @@ struct Tile {
     using C = Cfg<ID>;
     static constexpr int NB = C::NB;
     static constexpr int TILE = 256, THREADS = 128, EPT = 2, NW = THREADS / 32;
-    static constexpr int OSTR = (C::DIMO % 2 == 0) ? C::DIMO + 1 : C::DIMO;  // odd row stride: conflict-free scalar STS
-    static constexpr int GSTR = (C::DIMG % 2 == 0) ? C::DIMG + 1 : C::DIMG;
+    // rows that are 16-byte multiples are staged unpadded and moved with 128-bit accesses; others
+    // get an odd row stride (conflict-free scalar STS)
+    static constexpr int OSTR = (C::DIMO % 4 == 0) ? C::DIMO : ((C::DIMO % 2 == 0) ? C::DIMO + 1 : C::DIMO);
+    static constexpr int GSTR = (C::DIMG % 4 == 0) ? C::DIMG : ((C::DIMG % 2 == 0) ? C::DIMG + 1 : C::DIMG);
     static constexpr int STAGE = 32 * OSTR;
     static constexpr int W_COL = Col<NB, THREADS>::kFields * THREADS;  // private worker columns, aliased with the stage
     static constexpr int W_STAGE = (NW * STAGE > W_COL) ? NW * STAGE : W_COL;
@@ -279,17 +281,41 @@ struct Tile {
 // flush `nv` staged rows (row stride SSTR in shared memory) of W floats each to a contiguous global range
 template <int W, int SSTR>
 __device__ __forceinline__ void flush_rows(const float* stage, float* __restrict__ dst, int nv, int lane) {
-    const int total = nv * W;
-    for (int idx = lane; idx < total; idx += 32) {
-        const int row = idx / W, col = idx - row * W;
-        dst[idx] = stage[row * SSTR + col];
+    if constexpr (W % 4 == 0) {
+        // rows are 16-byte multiples: the stage is a linear image of the global range -> 128-bit copies
+        static_assert(SSTR == W, "vector path needs unpadded rows");
+        const int total4 = nv * (W / 4);
+        const float4* s4 = reinterpret_cast<const float4*>(stage);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = lane; i < total4; i += 32) d4[i] = s4[i];
+    } else {
+        const int total = nv * W;
+        for (int idx = lane; idx < total; idx += 32) {
+            const int row = idx / W, col = idx - row * W;
+            dst[idx] = stage[row * SSTR + col];
+        }
+    }
+}
+
+// write one row of W floats produced by `gen(put)` into the warp's stage at row `lane`
+template <int W, int SSTR, class Gen>
+__device__ __forceinline__ void stage_row(float* stage, int lane, Gen&& gen) {
+    if constexpr (W % 4 == 0) {
+        float row[W];
+        gen([&](int c, float v) { row[c] = v; });
+        float4* s4 = reinterpret_cast<float4*>(stage) + lane * (W / 4);
+#pragma unroll
+        for (int j = 0; j < W / 4; ++j) s4[j] = make_float4(row[4 * j], row[4 * j + 1], row[4 * j + 2], row[4 * j + 3]);
+    } else {
+        float* srow = stage + lane * SSTR;
+        gen([&](int c, float v) { srow[c] = v; });
     }
 }
 
 // RobotEnv.reset for one env of a tile: kept out of line (it is rare and large: Philox, log, sincos)
 template <int ID>
 __device__ __noinline__ void reset_in_tile(uint32_t* __restrict__ st, const StepArgs& p, int64_t gi, int64_t li, Grip& gr,
-                                           float* blk_col /* s_blk + le, stride TILE */, int& nb, uint32_t& touch_now, uint32_t& touch_ever) {
+                                           float* blk_col /* s_blk + le, stride TILE */, int& nb, uint32_t& touch_now, uint32_t& touch_ever, uint32_t& priv) {
     using C = Cfg<ID>;
     constexpr int NB = C::NB;
     constexpr int NF = num_fields<NB>();
@@ -312,7 +338,7 @@ __device__ __noinline__ void reset_in_tile(uint32_t* __restrict__ st, const Step
         bb[0] = e.px[b]; bb[TILE] = e.py[b]; bb[2 * TILE] = e.pz[b]; bb[3 * TILE] = e.c[b]; bb[4 * TILE] = e.s[b];
         bb[5 * TILE] = e.vx[b]; bb[6 * TILE] = e.vy[b]; bb[7 * TILE] = e.vz[b]; bb[8 * TILE] = e.w[b];
     }
-    nb = e.nb; touch_now = e.touch_now; touch_ever = e.touch_ever;
+    nb = e.nb; touch_now = e.touch_now; touch_ever = e.touch_ever; priv = e.priv;
     if (p.reset_obs) write_row_obs<ID>(e, p.reset_obs + li * C::DIMO);
     if (p.reset_ag) write_row_ag<ID>(e, p.reset_ag + li * C::DIMG);
 }
@@ -509,18 +535,14 @@ __global__ void __launch_bounds__(128, 4) step_kernel_tiled(uint32_t* __restrict
                         e.vx[b] = bb[5 * TILE]; e.vy[b] = bb[6 * TILE]; e.vz[b] = bb[7 * TILE]; e.w[b] = bb[8 * TILE];
                     }
                     e.nb = nb[j];
-                    float* srow = my_stage + lane * T::OSTR;
-                    env_write_obs<ID>(e, [&](int c, float v) { srow[c] = v; });
+                    stage_row<C::DIMO, T::OSTR>(my_stage, lane, [&](auto&& put) { env_write_obs<ID>(e, put); });
                 }
                 __syncwarp();
                 flush_rows<C::DIMO, T::OSTR>(my_stage, p.obs + ((int64_t)k * p.B + rg0) * C::DIMO, nv, lane);
                 __syncwarp();
             }
             if (p.ag) {
-                if (live[j]) {
-                    float* srow = my_stage + lane * T::GSTR;
-                    env_write_ag<ID>(touch_now[j], touch_ever[j], [&](int c, float v) { srow[c] = v; });
-                }
+                if (live[j]) stage_row<C::DIMG, T::GSTR>(my_stage, lane, [&](auto&& put) { env_write_ag<ID>(touch_now[j], touch_ever[j], put); });
                 __syncwarp();
                 flush_rows<C::DIMG, T::GSTR>(my_stage, p.ag + ((int64_t)k * p.B + rg0) * C::DIMG, nv, lane);
                 __syncwarp();
@@ -529,8 +551,8 @@ __global__ void __launch_bounds__(128, 4) step_kernel_tiled(uint32_t* __restrict
                 n_ep += 1.f; n_su += (float)succ[j];
                 if (p.auto_reset) {
                     // RobotEnv.reset inside the kernel (rare: once per 50 steps and env)
-                    reset_in_tile<ID>(st, p, p.env0 + li, li, gr[j], s_blk + le, nb[j], touch_now[j], touch_ever[j]);
-                    succ[j] = 0; tt[j] = 0; priv[j] = 0;
+                    reset_in_tile<ID>(st, p, p.env0 + li, li, gr[j], s_blk + le, nb[j], touch_now[j], touch_ever[j], priv[j]);
+                    succ[j] = 0; tt[j] = 0;
                 }
             }
         }
@@ -881,12 +903,13 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
         } else {
             using T = Tile<ID>;
             static bool attr_set[BP_NUM_ENV_IDS] = {};
+            static const size_t pad = [] { const char* e = getenv("BP_SMEM_PAD"); return e ? (size_t)atoi(e) : (size_t)0; }();  // occupancy experiments
             if (!attr_set[ID]) {
-                cudaError_t e = cudaFuncSetAttribute(step_kernel_tiled<ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM);
+                cudaError_t e = cudaFuncSetAttribute(step_kernel_tiled<ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T::SMEM + pad));
                 if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
                 attr_set[ID] = true;
             }
-            step_kernel_tiled<ID><<<nblk(a.B, T::TILE), T::THREADS, T::SMEM, s>>>(h->d_state, a);
+            step_kernel_tiled<ID><<<nblk(a.B, T::TILE), T::THREADS, T::SMEM + pad, s>>>(h->d_state, a);
         }
         return (int)BP_OK;
     });
