@@ -25,7 +25,7 @@ BP_ERR_CUDA = -2
 BP_ERR_NOT_IMPLEMENTED = -3
 BP_ERR_NO_DEVICE = -4
 BP_NUM_STATS = 8
-STAT_NAMES = ("episodes", "successes", "steps", "invalid", "reward_sum", "worker_steps")
+STAT_NAMES = ("episodes", "successes", "steps", "invalid", "reward_sum", "worker_steps", "sched_iterations", "sched_passes")
 STATE_BYTES = 244
 
 # every symbol include/blockpuzzle_b200.h declares: (name, restype, argtypes)

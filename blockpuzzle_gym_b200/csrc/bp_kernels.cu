@@ -592,6 +592,12 @@ __global__ void __launch_bounds__(128, 4) step_kernel_tiled(uint32_t* __restrict
     }
 }
 
+}  // namespace bp
+
+#include "bp_async.cuh"
+
+namespace bp {
+
 template <int ID>
 __global__ void get_state_kernel(const uint32_t* st, int64_t B, bp_env_state* out) {
     using C = Cfg<ID>;
@@ -786,6 +792,65 @@ static int dispatch(int env_id, F&& f) {
 
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// BP_STEP_KERNEL = async (default) | tiled | simple
+static int step_kernel_choice() {
+    static const int v = [] {
+        const char* e = getenv("BP_STEP_KERNEL");
+        if (e && strcmp(e, "simple") == 0) return 2;
+        if (e && strcmp(e, "tiled") == 0) return 1;
+        return 0;
+    }();
+    return v;
+}
+
+template <class K>
+static int set_smem_attr(K kernel, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    return BP_OK;
+}
+
+static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
+    static const size_t pad = [] { const char* e = getenv("BP_SMEM_PAD"); return e ? (size_t)atoi(e) : (size_t)0; }();  // occupancy experiments
+    int rc = dispatch(h->env_id, [&](auto id) {
+        constexpr int ID = decltype(id)::value;
+        const int choice = step_kernel_choice();
+        if (choice == 2) {
+            constexpr size_t kSmem = sizeof(float) * Col<Cfg<ID>::NB, 128>::kFields * 128;
+            step_kernel_simple<ID><<<nblk(a.B, 128), 128, kSmem, s>>>(h->d_state, a);
+        } else if (choice == 1) {
+            using T = Tile<ID>;
+            static bool attr_set[BP_NUM_ENV_IDS] = {};
+            if (!attr_set[ID]) {
+                int r = set_smem_attr(step_kernel_tiled<ID>, T::SMEM + pad);
+                if (r != BP_OK) return r;
+                attr_set[ID] = true;
+            }
+            step_kernel_tiled<ID><<<nblk(a.B, T::TILE), T::THREADS, T::SMEM + pad, s>>>(h->d_state, a);
+        } else {
+            static const int e_sel = [] { const char* e = getenv("BP_ASYNC_E"); return e ? atoi(e) : kAsyncE; }();  // envs per lane (tuning)
+            auto go = [&](auto ec) -> int {
+                constexpr int E = decltype(ec)::value;
+                using A = Async<ID, E>;
+                static bool attr_set = false;
+                if (!attr_set) {
+                    int r = set_smem_attr(step_kernel_async<ID, E>, A::SMEM + pad);
+                    if (r != BP_OK) return r;
+                    attr_set = true;
+                }
+                step_kernel_async<ID, E><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, a);
+                return (int)BP_OK;
+            };
+            int r = e_sel == 2 ? go(std::integral_constant<int, 2>()) : e_sel == 3 ? go(std::integral_constant<int, 3>()) : go(std::integral_constant<int, 4>());
+            if (r != BP_OK) return r;
+        }
+        return (int)BP_OK;
+    });
+    if (rc != BP_OK) return rc;
+    CU(cudaGetLastError());
+    return BP_OK;
+}
+
 extern "C" {
 
 int bp_abi_version(void) { return BP_ABI_VERSION; }
@@ -889,40 +954,11 @@ int bp_reset(bp_handle* h, const uint8_t* d_mask, float* d_obs, float* d_ag, flo
     return BP_OK;
 }
 
-static bool use_simple_kernel() {
-    static const bool v = [] { const char* e = getenv("BP_STEP_KERNEL"); return e && strcmp(e, "simple") == 0; }();
-    return v;
-}
-
-static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
-    int rc = dispatch(h->env_id, [&](auto id) {
-        constexpr int ID = decltype(id)::value;
-        if (use_simple_kernel()) {
-            constexpr size_t kSmem = sizeof(float) * Col<Cfg<ID>::NB, 128>::kFields * 128;
-            step_kernel_simple<ID><<<nblk(a.B, 128), 128, kSmem, s>>>(h->d_state, a);
-        } else {
-            using T = Tile<ID>;
-            static bool attr_set[BP_NUM_ENV_IDS] = {};
-            static const size_t pad = [] { const char* e = getenv("BP_SMEM_PAD"); return e ? (size_t)atoi(e) : (size_t)0; }();  // occupancy experiments
-            if (!attr_set[ID]) {
-                cudaError_t e = cudaFuncSetAttribute(step_kernel_tiled<ID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T::SMEM + pad));
-                if (e != cudaSuccess) return fail(BP_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-                attr_set[ID] = true;
-            }
-            step_kernel_tiled<ID><<<nblk(a.B, T::TILE), T::THREADS, T::SMEM + pad, s>>>(h->d_state, a);
-        }
-        return (int)BP_OK;
-    });
-    if (rc != BP_OK) return rc;
-    CU(cudaGetLastError());
-    return BP_OK;
-}
-
 int bp_step(bp_handle* h, const float* d_actions, int K, float* d_obs, float* d_ag, float* d_reward,
             float* d_success, uint8_t* d_done, int auto_reset, float* d_reset_obs, float* d_reset_ag,
             float* d_actions_out, void* stream) {
     if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
-    if (K <= 0) return fail(BP_ERR_INVALID_ARG, "K must be positive");
+    if (K <= 0 || K > 65535) return fail(BP_ERR_INVALID_ARG, "K must be in 1..65535");
     CU(cudaSetDevice(h->device));
     StepArgs a{};
     a.actions = d_actions; a.obs = d_obs; a.ag = d_ag; a.reward = d_reward; a.success = d_success; a.done = d_done;
@@ -934,7 +970,7 @@ int bp_step(bp_handle* h, const float* d_actions, int K, float* d_obs, float* d_
 int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, float* h_ag, float* h_reward,
                  float* h_success, int auto_reset) {
     if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
-    if (K <= 0 || !h_actions) return fail(BP_ERR_INVALID_ARG, "bp_step_host needs actions and K > 0");
+    if (K <= 0 || K > 65535 || !h_actions) return fail(BP_ERR_INVALID_ARG, "bp_step_host needs actions and K in 1..65535");
     CU(cudaSetDevice(h->device));
     const int dimo = kDimO[h->env_id], dimg = kDimG[h->env_id];
     // chunk of envs: per env and step 4 (action) + dimo + dimg + 2 floats
