@@ -160,6 +160,9 @@ __device__ __forceinline__ void bp_normal2(uint32_t w0, uint32_t w1, float& z0, 
 }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+// BlockPhys v1.1: the fused multiply-adds of the spec are written explicitly (the file is compiled
+// with -fmad=false, so nothing else is ever contracted)
+#define F(a, b, c) __fmaf_rn((a), (b), (c))
 
 // ---------------------------------------------------------------- env state in registers
 template <int NB>
@@ -227,11 +230,12 @@ struct Col {
 };
 
 __device__ __forceinline__ void rot_apply(float& c, float& s, float dth) {
-    float c2 = c - s * dth;
-    float s2 = s + c * dth;
-    float n = sqrtf(c2 * c2 + s2 * s2);
-    c = c2 / n;
-    s = s2 / n;
+    float c2 = F(-s, dth, c);
+    float s2 = F(c, dth, s);
+    float n = sqrtf(F(c2, c2, s2 * s2));
+    float r = 1.0f / n;
+    c = c2 * r;
+    s = s2 * r;
 }
 
 struct Rect { float x, y, c, s, hx, hy; };
@@ -243,22 +247,22 @@ struct Sat { float ov[4], proj[4], rtA[4], rtB[4]; };
 // AA: A is axis-aligned (c = 1, s = 0), which makes cr = B.c, sr = B.s, proj[0] = dx, proj[1] = dy exactly.
 template <bool AA>
 __device__ __forceinline__ bool sat_eval(const Rect& A, const Rect& B, Sat& o) {
-    float cr = AA ? B.c : A.c * B.c + A.s * B.s;
-    float sr = AA ? B.s : A.c * B.s - A.s * B.c;
+    float cr = AA ? B.c : F(A.c, B.c, A.s * B.s);
+    float sr = AA ? B.s : F(A.c, B.s, -(A.s * B.c));
     float C = fabsf(cr), S = fabsf(sr);
     float dx = B.x - A.x, dy = B.y - A.y;
-    float RBu = B.hx * C + B.hy * S;
-    o.proj[0] = AA ? dx : dx * A.c + dy * A.s;
+    float RBu = F(B.hx, C, B.hy * S);
+    o.proj[0] = AA ? dx : F(dx, A.c, dy * A.s);
     o.ov[0] = (A.hx + RBu) - fabsf(o.proj[0]);
     if (!(o.ov[0] > -kMargin)) return false;
-    float RBv = B.hx * S + B.hy * C;
-    o.proj[1] = AA ? dy : dy * A.c - dx * A.s;
+    float RBv = F(B.hx, S, B.hy * C);
+    o.proj[1] = AA ? dy : F(dy, A.c, -(dx * A.s));
     o.ov[1] = (A.hy + RBv) - fabsf(o.proj[1]);
     if (!(o.ov[1] > -kMargin)) return false;
-    float RAu = A.hx * C + A.hy * S;
-    float RAv = A.hx * S + A.hy * C;
-    o.proj[2] = dx * B.c + dy * B.s;
-    o.proj[3] = dy * B.c - dx * B.s;
+    float RAu = F(A.hx, C, A.hy * S);
+    float RAv = F(A.hx, S, A.hy * C);
+    o.proj[2] = F(dx, B.c, dy * B.s);
+    o.proj[3] = F(dy, B.c, -(dx * B.s));
     o.ov[2] = (RAu + B.hx) - fabsf(o.proj[2]);
     o.ov[3] = (RAv + B.hy) - fabsf(o.proj[3]);
     o.rtA[0] = A.hy; o.rtB[0] = RBv;
@@ -358,14 +362,14 @@ __device__ __forceinline__ void collide_finger_block(Grip& e, GripSub& st, const
     const float qo = f == 0 ? st.qo[0] : st.qo[1];
     float fdx = e.g[0] - st.gox;
     float fdy = (e.g[1] - st.goy) + sgn * (q_now - qo);
-    float rel = ((b.x - ox) - fdx) * nx + ((b.y - oy) - fdy) * ny;
+    float rel = F((b.x - ox) - fdx, nx, ((b.y - oy) - fdy) * ny);
     float cap = kDepen - rel;
     float lam = delta < cap ? delta : cap;
     if (!(lam > 0.0f)) return;
-    float D = 1.0f + kIInv * (rnB * rnB);
+    float D = F(kIInv, rnB * rnB, 1.0f);
     float l = lam / D;
-    b.x = b.x + nx * l;
-    b.y = b.y + ny * l;
+    b.x = F(nx, l, b.x);
+    b.y = F(ny, l, b.y);
     float dth = (kIInv * rnB) * l;
     if (dth != 0.0f) {
         rot_apply(b.c, b.s, dth);
@@ -411,19 +415,19 @@ __device__ __forceinline__ void collide_block_block(Blk& a, const float aox, con
     }
     float nx, ny, rnA, rnB;
     sat_contact(A, B, o, k, nx, ny, rnA, rnB);
-    float rel = ((b.x - box) - (a.x - aox)) * nx + ((b.y - boy) - (a.y - aoy)) * ny;
+    float rel = F((b.x - box) - (a.x - aox), nx, ((b.y - boy) - (a.y - aoy)) * ny);
     float cap = kDepen - rel;
     float lam = minxy < cap ? minxy : cap;
     if (!(lam > 0.0f)) return;
     float wA = pin == 1 ? 0.0f : 1.0f;
     float wB = pin == 2 ? 0.0f : 1.0f;
-    float D = (wA + wB) + kIInv * (wA * (rnA * rnA) + wB * (rnB * rnB));
+    float D = F(kIInv, F(wA, rnA * rnA, wB * (rnB * rnB)), wA + wB);
     float l = lam / D;
     float lA = wA * l, lB = wB * l;
-    a.x = a.x - nx * lA;
-    a.y = a.y - ny * lA;
-    b.x = b.x + nx * lB;
-    b.y = b.y + ny * lB;
+    a.x = F(-nx, lA, a.x);
+    a.y = F(-ny, lA, a.y);
+    b.x = F(nx, lB, b.x);
+    b.y = F(ny, lB, b.y);
     float dthA = -((kIInv * rnA) * lA);
     float dthB = (kIInv * rnB) * lB;
     if (dthA != 0.0f) { rot_apply(a.c, a.s, dthA); adth = adth + dthA; rotated = true; }
@@ -438,9 +442,9 @@ __device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const floa
     st.qo[0] = e.q[0]; st.qo[1] = e.q[1];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        float acc = kKW * (m[k] - e.g[k]) - kBW * e.gv[k];
-        e.gv[k] = e.gv[k] + acc * kH;
-        e.g[k] = e.g[k] + e.gv[k] * kH;
+        float acc = F(kKW, m[k] - e.g[k], -(kBW * e.gv[k]));
+        e.gv[k] = F(acc, kH, e.gv[k]);
+        e.g[k] = F(e.gv[k], kH, e.g[k]);
     }
     if (e.g[2] < kGZMin) {
         e.g[2] = kGZMin;
@@ -450,9 +454,9 @@ __device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const floa
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
             float q_old = e.q[f];
-            float acc = kKF * (ctrl[f] - e.q[f]) - kBF * e.qv[f];
-            e.qv[f] = e.qv[f] + acc * kH;
-            e.q[f] = e.q[f] + e.qv[f] * kH;
+            float acc = F(kKF, ctrl[f] - e.q[f], -(kBF * e.qv[f]));
+            e.qv[f] = F(acc, kH, e.qv[f]);
+            e.q[f] = F(e.qv[f], kH, e.q[f]);
             if (e.q[f] < 0.0f) { e.q[f] = 0.0f; if (e.qv[f] < 0.0f) e.qv[f] = 0.0f; }
             if (e.q[f] > kQMax) { e.q[f] = kQMax; if (e.qv[f] > 0.0f) e.qv[f] = 0.0f; }
             float cl = q_old - e.q[f];
@@ -476,9 +480,9 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB
         col.scr(i, 0) = b.x; col.scr(i, 1) = b.y; col.scr(i, 2) = b.z;
         float dth = 0.0f;
         b.vz = b.vz - kGH;
-        b.x = b.x + b.vx * kH;
-        b.y = b.y + b.vy * kH;
-        b.z = b.z + b.vz * kH;
+        b.x = F(b.vx, kH, b.x);
+        b.y = F(b.vy, kH, b.y);
+        b.z = F(b.vz, kH, b.z);
         if (b.w != 0.0f) {
             dth = b.w * kH;
             rot_apply(b.c, b.s, dth);
@@ -532,7 +536,7 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB
         b.vz = clampf((b.z - oz) * kInvH, -kVMax, kVMax);
         b.w = clampf(col.scr(i, 3) * kInvH, -kWMax, kWMax);
         if (sup >> i & 1u) {
-            float sp2 = b.vx * b.vx + b.vy * b.vy;
+            float sp2 = F(b.vx, b.vx, b.vy * b.vy);
             if (sp2 <= kFr * kFr) {
                 b.vx = 0.0f; b.vy = 0.0f;
             } else {
@@ -553,9 +557,9 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB
 // mocap target and finger actuator targets from the clipped action (fetch_env.py:170-185)
 template <bool BG>
 __device__ __forceinline__ void action_targets(const Grip& e, const float a[4], float m[3], float ctrl[2]) {
-    m[0] = clampf(e.g[0] + a[0] * kPosScale, kWsXLo, kWsXHi);
-    m[1] = clampf(e.g[1] + a[1] * kPosScale, kWsYLo, kWsYHi);
-    m[2] = clampf(e.g[2] + a[2] * kPosScale, kGZMin, kWsZHi);
+    m[0] = clampf(F(a[0], kPosScale, e.g[0]), kWsXLo, kWsXHi);
+    m[1] = clampf(F(a[1], kPosScale, e.g[1]), kWsYLo, kWsYHi);
+    m[2] = clampf(F(a[2], kPosScale, e.g[2]), kGZMin, kWsZHi);
     float ga = BG ? 0.0f : a[3];
     ctrl[0] = clampf(e.q[0] + ga, 0.0f, kCtrlMax);
     ctrl[1] = clampf(e.q[1] + ga, 0.0f, kCtrlMax);

@@ -231,25 +231,28 @@ void bpo_sim_init(bpo_sim* sim, int env_id) {
 }
 
 static float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+/* BlockPhys v1.1: the fused multiply-adds of the spec are written explicitly (single rounding) */
+#define F(a, b, c) fmaf((a), (b), (c))
 
 /* fetch_env.py:170-185 + gym.envs.robotics.utils.ctrl_set_action / mocap_set_action
  * [upstream, recalled]: mocap is snapped to the welded body, then moved by
  * 0.05*a[:3]; finger position-actuator target = qpos + a[3], clipped to ctrlrange. */
 void bpo_sim_set_action(bpo_sim* sim, const float a[4]) {
-    sim->m[0] = clampf(sim->g[0] + a[0] * POS_SCALE, WS_XLO, WS_XHI);
-    sim->m[1] = clampf(sim->g[1] + a[1] * POS_SCALE, WS_YLO, WS_YHI);
-    sim->m[2] = clampf(sim->g[2] + a[2] * POS_SCALE, GZ_MIN, WS_ZHI);
+    sim->m[0] = clampf(F(a[0], POS_SCALE, sim->g[0]), WS_XLO, WS_XHI);
+    sim->m[1] = clampf(F(a[1], POS_SCALE, sim->g[1]), WS_YLO, WS_YHI);
+    sim->m[2] = clampf(F(a[2], POS_SCALE, sim->g[2]), GZ_MIN, WS_ZHI);
     float ga = sim->block_gripper ? 0.0f : a[3]; /* fetch_env.py:179-180 */
     sim->ctrl[0] = clampf(sim->q[0] + ga, 0.0f, CTRL_MAX);
     sim->ctrl[1] = clampf(sim->q[1] + ga, 0.0f, CTRL_MAX);
 }
 
 static void rot_apply(bpo_block* b, float dth) {
-    float c2 = b->c - b->s * dth;
-    float s2 = b->s + b->c * dth;
-    float n = sqrtf(c2 * c2 + s2 * s2);
-    b->c = c2 / n;
-    b->s = s2 / n;
+    float c2 = F(-b->s, dth, b->c);
+    float s2 = F(b->c, dth, b->s);
+    float n = sqrtf(F(c2, c2, s2 * s2));
+    float r = 1.0f / n;
+    b->c = c2 * r;
+    b->s = s2 * r;
 }
 
 typedef struct { float x, y, c, s, hx, hy; } rect2;
@@ -263,18 +266,18 @@ typedef struct {
 } sat2;
 
 static void sat2_eval(const rect2* A, const rect2* B, sat2* o) {
-    float cr = A->c * B->c + A->s * B->s;
-    float sr = A->c * B->s - A->s * B->c;
+    float cr = F(A->c, B->c, A->s * B->s);
+    float sr = F(A->c, B->s, -(A->s * B->c));
     float C = fabsf(cr), S = fabsf(sr);
     float dx = B->x - A->x, dy = B->y - A->y;
-    float RBu = B->hx * C + B->hy * S; /* B along A.u */
-    float RBv = B->hx * S + B->hy * C; /* B along A.v */
-    float RAu = A->hx * C + A->hy * S; /* A along B.u */
-    float RAv = A->hx * S + A->hy * C; /* A along B.v */
-    o->proj[0] = dx * A->c + dy * A->s;
-    o->proj[1] = dy * A->c - dx * A->s;
-    o->proj[2] = dx * B->c + dy * B->s;
-    o->proj[3] = dy * B->c - dx * B->s;
+    float RBu = F(B->hx, C, B->hy * S); /* B along A.u */
+    float RBv = F(B->hx, S, B->hy * C); /* B along A.v */
+    float RAu = F(A->hx, C, A->hy * S); /* A along B.u */
+    float RAv = F(A->hx, S, A->hy * C); /* A along B.v */
+    o->proj[0] = F(dx, A->c, dy * A->s);
+    o->proj[1] = F(dy, A->c, -(dx * A->s));
+    o->proj[2] = F(dx, B->c, dy * B->s);
+    o->proj[3] = F(dy, B->c, -(dx * B->s));
     o->ov[0] = (A->hx + RBu) - fabsf(o->proj[0]);
     o->ov[1] = (A->hy + RBv) - fabsf(o->proj[1]);
     o->ov[2] = (RAu + B->hx) - fabsf(o->proj[2]);
@@ -396,14 +399,14 @@ static void collide_finger_block(bpo_sim* sim, int f, int bi, sub_tmp* st) {
     float sgn = f == 0 ? 1.0f : -1.0f;
     float fdx = sim->g[0] - st->g_old[0];
     float fdy = (sim->g[1] - st->g_old[1]) + sgn * (sim->q[f] - st->q_old[f]);
-    float rel = ((b->pos[0] - tmp[bi].old[0]) - fdx) * nx + ((b->pos[1] - tmp[bi].old[1]) - fdy) * ny;
+    float rel = F((b->pos[0] - tmp[bi].old[0]) - fdx, nx, ((b->pos[1] - tmp[bi].old[1]) - fdy) * ny);
     float cap = DEPEN - rel;
     float lam = delta < cap ? delta : cap;
     if (!(lam > 0.0f)) return;
-    float D = 1.0f + IINV * (rnB * rnB);
+    float D = F(IINV, rnB * rnB, 1.0f);
     float l = lam / D;
-    b->pos[0] = b->pos[0] + nx * l;
-    b->pos[1] = b->pos[1] + ny * l;
+    b->pos[0] = F(nx, l, b->pos[0]);
+    b->pos[1] = F(ny, l, b->pos[1]);
     float dth = (IINV * rnB) * l;
     if (dth != 0.0f) {
         rot_apply(b, dth);
@@ -449,20 +452,20 @@ static void collide_block_block(bpo_sim* sim, int i, int j, blk_tmp* tmp) {
     }
     float nx, ny, rnA, rnB;
     sat2_contact(&A, &B, &o, k, &nx, &ny, &rnA, &rnB);
-    float rel = ((b->pos[0] - tmp[j].old[0]) - (a->pos[0] - tmp[i].old[0])) * nx +
-                ((b->pos[1] - tmp[j].old[1]) - (a->pos[1] - tmp[i].old[1])) * ny;
+    float rel = F((b->pos[0] - tmp[j].old[0]) - (a->pos[0] - tmp[i].old[0]), nx,
+                  ((b->pos[1] - tmp[j].old[1]) - (a->pos[1] - tmp[i].old[1])) * ny);
     float cap = DEPEN - rel;
     float lam = minxy < cap ? minxy : cap;
     if (!(lam > 0.0f)) return;
     float wA = pin == 1 ? 0.0f : 1.0f;
     float wB = pin == 2 ? 0.0f : 1.0f;
-    float D = (wA + wB) + IINV * (wA * (rnA * rnA) + wB * (rnB * rnB));
+    float D = F(IINV, F(wA, rnA * rnA, wB * (rnB * rnB)), wA + wB);
     float l = lam / D;
     float lA = wA * l, lB = wB * l;
-    a->pos[0] = a->pos[0] - nx * lA;
-    a->pos[1] = a->pos[1] - ny * lA;
-    b->pos[0] = b->pos[0] + nx * lB;
-    b->pos[1] = b->pos[1] + ny * lB;
+    a->pos[0] = F(-nx, lA, a->pos[0]);
+    a->pos[1] = F(-ny, lA, a->pos[1]);
+    b->pos[0] = F(nx, lB, b->pos[0]);
+    b->pos[1] = F(ny, lB, b->pos[1]);
     float dthA = -((IINV * rnA) * lA);
     float dthB = (IINV * rnB) * lB;
     if (dthA != 0.0f) { rot_apply(a, dthA); tmp[i].dth = tmp[i].dth + dthA; }
@@ -482,9 +485,9 @@ void bpo_sim_substep(bpo_sim* sim) {
     st.q_old[0] = sim->q[0]; st.q_old[1] = sim->q[1];
     /* 1. gripper: critically damped tracking of the mocap target (weld, shared.xml:48-50) */
     for (int k = 0; k < 3; ++k) {
-        float acc = KW * (sim->m[k] - sim->g[k]) - BW * sim->gv[k];
-        sim->gv[k] = sim->gv[k] + acc * H;
-        sim->g[k] = sim->g[k] + sim->gv[k] * H;
+        float acc = F(KW, sim->m[k] - sim->g[k], -(BW * sim->gv[k]));
+        sim->gv[k] = F(acc, H, sim->gv[k]);
+        sim->g[k] = F(sim->gv[k], H, sim->g[k]);
     }
     if (sim->g[2] < GZ_MIN) {
         sim->g[2] = GZ_MIN;
@@ -494,9 +497,9 @@ void bpo_sim_substep(bpo_sim* sim) {
     if (!sim->block_gripper) {
         for (int f = 0; f < 2; ++f) {
             float q_old = sim->q[f];
-            float acc = KF * (sim->ctrl[f] - sim->q[f]) - BF * sim->qv[f];
-            sim->qv[f] = sim->qv[f] + acc * H;
-            sim->q[f] = sim->q[f] + sim->qv[f] * H;
+            float acc = F(KF, sim->ctrl[f] - sim->q[f], -(BF * sim->qv[f]));
+            sim->qv[f] = F(acc, H, sim->qv[f]);
+            sim->q[f] = F(sim->qv[f], H, sim->q[f]);
             if (sim->q[f] < 0.0f) { sim->q[f] = 0.0f; if (sim->qv[f] < 0.0f) sim->qv[f] = 0.0f; }
             if (sim->q[f] > QMAX) { sim->q[f] = QMAX; if (sim->qv[f] > 0.0f) sim->qv[f] = 0.0f; }
             float cl = q_old - sim->q[f];
@@ -510,9 +513,9 @@ void bpo_sim_substep(bpo_sim* sim) {
         tmp[i].dth = 0.0f;
         tmp[i].supported = 0;
         b->vel[2] = b->vel[2] - GH;
-        b->pos[0] = b->pos[0] + b->vel[0] * H;
-        b->pos[1] = b->pos[1] + b->vel[1] * H;
-        b->pos[2] = b->pos[2] + b->vel[2] * H;
+        b->pos[0] = F(b->vel[0], H, b->pos[0]);
+        b->pos[1] = F(b->vel[1], H, b->pos[1]);
+        b->pos[2] = F(b->vel[2], H, b->pos[2]);
         if (b->w != 0.0f) {
             float dth = b->w * H;
             rot_apply(b, dth);
@@ -551,7 +554,7 @@ void bpo_sim_substep(bpo_sim* sim) {
         for (int k = 0; k < 3; ++k) b->vel[k] = clampf(b->vel[k], -VMAX, VMAX);
         b->w = clampf(b->w, -WMAX, WMAX);
         if (tmp[i].supported) {
-            float sp2 = b->vel[0] * b->vel[0] + b->vel[1] * b->vel[1];
+            float sp2 = F(b->vel[0], b->vel[0], b->vel[1] * b->vel[1]);
             if (sp2 <= FR * FR) {
                 b->vel[0] = 0.0f; b->vel[1] = 0.0f;
             } else {
