@@ -344,7 +344,7 @@ __device__ __noinline__ void reset_in_tile(uint32_t* __restrict__ st, const Step
 }
 
 template <int ID>
-__global__ void __launch_bounds__(128, 4) step_kernel_tiled(uint32_t* __restrict__ st, StepArgs p) {
+__global__ void __launch_bounds__(128, 4) step_kernel_tiled(uint32_t* __restrict__ st, const __grid_constant__ StepArgs p) {
     using T = Tile<ID>;
     using C = Cfg<ID>;
     constexpr int NB = C::NB, TILE = T::TILE, EPT = T::EPT, NW = T::NW;
@@ -838,7 +838,20 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                     if (r != BP_OK) return r;
                     attr_set = true;
                 }
-                step_kernel_async<ID, E><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, a);
+                // the kernel keeps the reward / success bits of at most kMaxFused steps on chip: split longer K
+                for (int k0 = 0; k0 < a.K; k0 += kMaxFused) {
+                    StepArgs c = a;
+                    c.K = (a.K - k0) < kMaxFused ? (a.K - k0) : kMaxFused;
+                    const int64_t off = (int64_t)k0 * a.B;
+                    if (a.actions) c.actions = a.actions + off * 4;
+                    if (a.actions_out) c.actions_out = a.actions_out + off * 4;
+                    if (a.obs) c.obs = a.obs + off * Cfg<ID>::DIMO;
+                    if (a.ag) c.ag = a.ag + off * Cfg<ID>::DIMG;
+                    if (a.reward) c.reward = a.reward + off;
+                    if (a.success) c.success = a.success + off;
+                    if (a.done) c.done = a.done + off;
+                    step_kernel_async<ID, E><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
+                }
                 return (int)BP_OK;
             };
             int r = e_sel == 2 ? go(std::integral_constant<int, 2>()) : e_sel == 3 ? go(std::integral_constant<int, 3>()) : go(std::integral_constant<int, 4>());
