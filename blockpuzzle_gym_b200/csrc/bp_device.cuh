@@ -446,21 +446,27 @@ __device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const floa
         e.gv[k] = F(acc, kH, e.gv[k]);
         e.g[k] = F(e.gv[k], kH, e.g[k]);
     }
-    if (e.g[2] < kGZMin) {
-        e.g[2] = kGZMin;
-        if (e.gv[2] < 0.0f) e.gv[2] = 0.0f;
+    // the limits below are written as selects (no divergent branches in the 20-substep loop)
+    {
+        const bool low = e.g[2] < kGZMin;
+        e.gv[2] = (low && e.gv[2] < 0.0f) ? 0.0f : e.gv[2];
+        e.g[2] = low ? kGZMin : e.g[2];
     }
     if (!BG) {
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
-            float q_old = e.q[f];
-            float acc = F(kKF, ctrl[f] - e.q[f], -(kBF * e.qv[f]));
-            e.qv[f] = F(acc, kH, e.qv[f]);
-            e.q[f] = F(e.qv[f], kH, e.q[f]);
-            if (e.q[f] < 0.0f) { e.q[f] = 0.0f; if (e.qv[f] < 0.0f) e.qv[f] = 0.0f; }
-            if (e.q[f] > kQMax) { e.q[f] = kQMax; if (e.qv[f] > 0.0f) e.qv[f] = 0.0f; }
-            float cl = q_old - e.q[f];
-            st.closed[f] = cl > 0.0f ? cl : 0.0f;
+            const float q_old = e.q[f];
+            const float acc = F(kKF, ctrl[f] - e.q[f], -(kBF * e.qv[f]));
+            float qv = F(acc, kH, e.qv[f]);
+            float q = F(qv, kH, e.q[f]);
+            const bool low = q < 0.0f;
+            qv = (low && qv < 0.0f) ? 0.0f : qv;
+            q = low ? 0.0f : q;
+            const bool high = q > kQMax;
+            qv = (high && qv > 0.0f) ? 0.0f : qv;
+            q = high ? kQMax : q;
+            e.q[f] = q; e.qv[f] = qv;
+            st.closed[f] = fmaxf(q_old - q, 0.0f);
         }
     }
 }
