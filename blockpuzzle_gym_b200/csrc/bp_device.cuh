@@ -495,12 +495,14 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB
             rotated = true;
         }
         col.scr(i, 3) = dth;
-        if (over_table(b.x, b.y)) {
-            if (b.z - kZRest < kMargin) contacts |= pair_bit(1, 2) << i;  // "table" -> 1 (fetch_env.py:113-114)
-            if (b.z < kZRest) { b.z = kZRest; sup |= 1u << i; }
-        } else if (b.z < kZFloor) {
-            b.z = kZFloor;  // floor0 maps to None: no touch entry
-            sup |= 1u << i;
+        {   // written as selects: no divergent branches
+            const bool ot = over_table(b.x, b.y);
+            const bool touch_t = ot && (b.z - kZRest < kMargin);   // "table" -> 1 (fetch_env.py:113-114)
+            const bool on_t = ot && b.z < kZRest;
+            const bool on_f = !ot && b.z < kZFloor;                // floor0 maps to None: no touch entry
+            contacts |= touch_t ? (pair_bit(1, 2) << i) : 0u;
+            b.z = on_t ? kZRest : (on_f ? kZFloor : b.z);
+            sup |= (on_t || on_f) ? (1u << i) : 0u;
         }
         col.store_pose(i, b);
     }
@@ -541,18 +543,19 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB
         b.vy = clampf((b.y - oy) * kInvH, -kVMax, kVMax);
         b.vz = clampf((b.z - oz) * kInvH, -kVMax, kVMax);
         b.w = clampf(col.scr(i, 3) * kInvH, -kWMax, kWMax);
-        if (sup >> i & 1u) {
-            float sp2 = F(b.vx, b.vx, b.vy * b.vy);
-            if (sp2 <= kFr * kFr) {
-                b.vx = 0.0f; b.vy = 0.0f;
-            } else {
+        {
+            const bool supd = (sup >> i & 1u) != 0u;
+            const float sp2 = F(b.vx, b.vx, b.vy * b.vy);
+            if (supd && sp2 > kFr * kFr) {      // sliding: the only branch (sqrt + divide)
                 float sp = sqrtf(sp2);
                 float kf = (sp - kFr) / sp;
                 b.vx = b.vx * kf;
                 b.vy = b.vy * kf;
+            } else if (supd) {
+                b.vx = 0.0f; b.vy = 0.0f;
             }
-            if (fabsf(b.w) <= kFrW) b.w = 0.0f;
-            else b.w = b.w > 0.0f ? b.w - kFrW : b.w + kFrW;
+            const float wdec = b.w > 0.0f ? b.w - kFrW : b.w + kFrW;
+            b.w = supd ? ((fabsf(b.w) <= kFrW) ? 0.0f : wdec) : b.w;
         }
         same = same && b.vx == 0.0f && b.vy == 0.0f && b.vz == 0.0f && b.w == 0.0f;
         col.store(i, b);
