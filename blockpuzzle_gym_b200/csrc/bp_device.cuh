@@ -246,19 +246,19 @@ struct Sat { float ov[4], proj[4], rtA[4], rtB[4]; };
 // is: the pair then cannot be in contact, exactly as min(ovz, ov[0..3]) > -margin would decide.
 // AA: A is axis-aligned (c = 1, s = 0), which makes cr = B.c, sr = B.s, proj[0] = dx, proj[1] = dy exactly.
 template <bool AA>
-__device__ __forceinline__ bool sat_eval(const Rect& A, const Rect& B, Sat& o) {
+__device__ __forceinline__ bool sat_eval(const Rect& A, const Rect& B, Sat& o, const float ovz) {
     float cr = AA ? B.c : F(A.c, B.c, A.s * B.s);
     float sr = AA ? B.s : F(A.c, B.s, -(A.s * B.c));
     float C = fabsf(cr), S = fabsf(sr);
     float dx = B.x - A.x, dy = B.y - A.y;
     float RBu = F(B.hx, C, B.hy * S);
-    o.proj[0] = AA ? dx : F(dx, A.c, dy * A.s);
-    o.ov[0] = (A.hx + RBu) - fabsf(o.proj[0]);
-    if (!(o.ov[0] > -kMargin)) return false;
     float RBv = F(B.hx, S, B.hy * C);
+    o.proj[0] = AA ? dx : F(dx, A.c, dy * A.s);
     o.proj[1] = AA ? dy : F(dy, A.c, -(dx * A.s));
+    o.ov[0] = (A.hx + RBu) - fabsf(o.proj[0]);
     o.ov[1] = (A.hy + RBv) - fabsf(o.proj[1]);
-    if (!(o.ov[1] > -kMargin)) return false;
+    // one branch for the three cheap axes (z and A's two): a single reconvergence point per pair
+    if (!(ovz > -kMargin) || !(o.ov[0] > -kMargin) || !(o.ov[1] > -kMargin)) return false;
     float RAu = F(A.hx, C, A.hy * S);
     float RAv = F(A.hx, S, A.hy * C);
     o.proj[2] = F(dx, B.c, dy * B.s);
@@ -320,9 +320,8 @@ __device__ __forceinline__ void collide_finger_block(Grip& e, GripSub& st, const
     Rect B{b.x, b.y, b.c, b.s, kHB, kHB};
     float dz = b.z - az;
     float ovz = (kFZ + kHB) - fabsf(dz);
-    if (!(ovz > -kMargin)) return;
     Sat o;
-    if (!sat_eval<true>(A, B, o)) return;
+    if (!sat_eval<true>(A, B, o, ovz)) return;
     float minxy;
     int k = sat_argmin(o, minxy);
     float minov = ovz < minxy ? ovz : minxy;
@@ -386,9 +385,8 @@ __device__ __forceinline__ void collide_block_block(Blk& a, const float aox, con
     Rect B{b.x, b.y, b.c, b.s, kHB, kHB};
     float dz = b.z - a.z;
     float ovz = kTwoHB - fabsf(dz);
-    if (!(ovz > -kMargin)) return;
     Sat o;
-    if (!sat_eval<false>(A, B, o)) return;
+    if (!sat_eval<false>(A, B, o, ovz)) return;
     float minxy;
     int k = sat_argmin(o, minxy);
     float minov = ovz < minxy ? ovz : minxy;
