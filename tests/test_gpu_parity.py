@@ -65,18 +65,28 @@ def test_4096_envs_fused_philox_replay():
     env, ref = _make("BlocksTouch-v0", B, seed=0)
     env.reset(); ref.reset()
     for launch in range(2):
-        out = env.step_fused(None, K=K, auto_reset=True, want_actions=True, want_reset_obs=True)
+        out = env.step_fused(None, K=K, auto_reset=True, want_actions=True, want_reset_obs=True, want_done=True)
         acts = out["actions"].cpu().numpy()
         obs = out["observation"].cpu().numpy(); ag = out["achieved_goal"].cpu().numpy()
         rew = out["reward"].cpu().numpy(); suc = out["is_success"].cpu().numpy()
+        done = out["done"].cpu().numpy()
+        robs = out["reset_observation"].cpu().numpy(); rag = out["reset_achieved_goal"].cpu().numpy()
+        n_done = 0
         for k in range(K):
             a = ref.random_actions()
             assert np.array_equal(a, acts[k])
+            t_before = ref.get_state()["t"]
             o2, ag2, r2, s2, ro2, ra2 = ref.step(a, auto_reset=True)
             assert np.array_equal(obs[k], o2), (launch, k)
             assert np.array_equal(ag[k], ag2), (launch, k)
             assert np.array_equal(rew[k].view(np.uint32), r2.view(np.uint32))
             assert np.array_equal(suc[k], s2)
+            d2 = t_before == 49                                     # TimeLimit: done on the 50th step
+            assert np.array_equal(done[k].astype(bool), d2)
+            if d2.any():                                            # fresh observation of the in-kernel reset
+                assert np.array_equal(robs[d2], ro2[d2]) and np.array_equal(rag[d2], ra2[d2])
+                n_done += int(d2.sum())
+        assert n_done == B                                          # every env finishes exactly one episode per 64-step launch here
         _assert_state_equal(env, ref, f"launch {launch}")
     st = env.stats()
     assert st["steps"] == 2 * K * B
@@ -260,9 +270,10 @@ def test_gym_single_env_surface():
         assert env.compute_reward(o["achieved_goal"], o["desired_goal"], info) == r
 
 
-def test_simple_and_tiled_kernels_agree():
-    """The tiled kernel's quiet path must be result-neutral: BP_STEP_KERNEL=simple runs the full physics
-    for every env-step; both must leave byte-identical state and outputs (checked via hashes)."""
+def test_all_step_kernels_agree():
+    """The quiet path and the schedulers must be result-neutral: BP_STEP_KERNEL=simple runs the full physics
+    for every env-step in order; the warp-autonomous (default) and the tiled kernel must leave byte-identical
+    state and outputs (checked via hashes)."""
     import hashlib
     import subprocess
     import sys
@@ -277,7 +288,7 @@ def test_simple_and_tiled_kernels_agree():
         "print(h.hexdigest())\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for mode in ("tiled", "simple"):
+    for mode in ("async", "tiled", "simple"):
         env = dict(os.environ, BP_STEP_KERNEL=mode, PYTHONPATH=root)
         outs.append(subprocess.check_output([sys.executable, "-c", code], env=env, cwd=root).decode().strip().splitlines()[-1])
-    assert outs[0] == outs[1]
+    assert outs[0] == outs[1] == outs[2]
