@@ -43,6 +43,7 @@ SYMBOLS = {
     "bp_reset": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "bp_step": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "bp_step_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i]),
+    "bp_rollout": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bp_set_test": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "bp_increase_difficulty": (_i, [_vp, C.POINTER(_i)]),
     "bp_get_difficulty": (_i, [_vp, C.POINTER(_i)]),

@@ -107,7 +107,7 @@ __device__ __forceinline__ void write_row_goal(float* row) {
 }
 
 template <int ID>
-__global__ void reset_kernel(uint32_t* st, int64_t B, const uint8_t* mask, Ranges rg, float* obs, float* ag, float* g) {
+__global__ void reset_kernel(uint32_t* st, int64_t B, const uint8_t* mask, Ranges rg, float* obs, float* ag, float* g, int64_t oag_stride) {
     using C = Cfg<ID>;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
@@ -116,21 +116,21 @@ __global__ void reset_kernel(uint32_t* st, int64_t B, const uint8_t* mask, Range
     load_env<C::NB>(st, B, i, e);
     env_reset<ID>(e, rg);
     store_env<C::NB>(st, B, i, e);
-    if (obs) write_row_obs<ID>(e, obs + i * C::DIMO);
-    if (ag) write_row_ag<ID>(e, ag + i * C::DIMG);
+    if (obs) write_row_obs<ID>(e, obs + i * oag_stride * C::DIMO);  // oag_stride rows between envs (1, or T + 1 for episode tensors)
+    if (ag) write_row_ag<ID>(e, ag + i * oag_stride * C::DIMG);
     if (g) write_row_goal<ID>(g + i * C::DIMG);
 }
 
 // set_test: fetch_env.py:365-368, 443-446 (stale obs, appendix A4); Variation :641-644
 template <int ID>
-__global__ void set_test_kernel(uint32_t* st, int64_t B, Ranges rg, float* obs, float* ag, float* g) {
+__global__ void set_test_kernel(uint32_t* st, int64_t B, Ranges rg, float* obs, float* ag, float* g, int64_t oag_stride) {
     using C = Cfg<ID>;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     Env<C::NB> e;
     load_env<C::NB>(st, B, i, e);
-    if (obs) write_row_obs<ID>(e, obs + i * C::DIMO);
-    if (ag) write_row_ag<ID>(e, ag + i * C::DIMG);
+    if (obs) write_row_obs<ID>(e, obs + i * oag_stride * C::DIMO);
+    if (ag) write_row_ag<ID>(e, ag + i * oag_stride * C::DIMG);
     if (g) write_row_goal<ID>(g + i * C::DIMG);
     if (!C::VAR) {
         randomize_objects<ID>(e, e.episode - 1u, true, rg);
@@ -156,7 +156,21 @@ struct StepArgs {
     int K;
     int auto_reset;
     Ranges rg;
+    // output addressing.  layout 0 (time-major): row (k0 + k) * B + li for every tensor.
+    // layout 1 (batch-major episode, async kernel only): per-step tensors [B][Ktot] -> row li * Ktot + k0 + k;
+    // obs / ag are [B][Ktot + 1] with the reset observation in slot 0 -> row li * (Ktot + 1) + k0 + k + 1.
+    int layout;
+    int k0;
+    int Ktot;
+    float* goal_out;       // layout 1: desired_goal rows [B][Ktot][DIMG] (nullable)
 };
+
+__device__ __forceinline__ int64_t step_row(const StepArgs& p, int k, int64_t li) {
+    return p.layout ? li * p.Ktot + (p.k0 + k) : (int64_t)(p.k0 + k) * p.B + li;
+}
+__device__ __forceinline__ int64_t obs_row(const StepArgs& p, int k, int64_t li) {
+    return p.layout ? li * (p.Ktot + 1) + (p.k0 + k) + 1 : (int64_t)(p.k0 + k) * p.B + li;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -815,6 +829,7 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
     int rc = dispatch(h->env_id, [&](auto id) {
         constexpr int ID = decltype(id)::value;
         const int choice = step_kernel_choice();
+        if (a.layout != 0 && choice != 0) return fail(BP_ERR_INVALID_ARG, "the batch-major episode layout needs the async step kernel");
         if (choice == 2) {
             constexpr size_t kSmem = sizeof(float) * Col<Cfg<ID>::NB, 128>::kFields * 128;
             step_kernel_simple<ID><<<nblk(a.B, 128), 128, kSmem, s>>>(h->d_state, a);
@@ -842,14 +857,7 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                 for (int k0 = 0; k0 < a.K; k0 += kMaxFused) {
                     StepArgs c = a;
                     c.K = (a.K - k0) < kMaxFused ? (a.K - k0) : kMaxFused;
-                    const int64_t off = (int64_t)k0 * a.B;
-                    if (a.actions) c.actions = a.actions + off * 4;
-                    if (a.actions_out) c.actions_out = a.actions_out + off * 4;
-                    if (a.obs) c.obs = a.obs + off * Cfg<ID>::DIMO;
-                    if (a.ag) c.ag = a.ag + off * Cfg<ID>::DIMG;
-                    if (a.reward) c.reward = a.reward + off;
-                    if (a.success) c.success = a.success + off;
-                    if (a.done) c.done = a.done + off;
+                    c.k0 = a.k0 + k0;
                     step_kernel_async<ID, E><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
                 }
                 return (int)BP_OK;
@@ -959,7 +967,7 @@ int bp_reset(bp_handle* h, const uint8_t* d_mask, float* d_obs, float* d_ag, flo
     CU(cudaSetDevice(h->device));
     Ranges rg = ranges_of(h);
     int rc = dispatch(h->env_id, [&](auto id) {
-        reset_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, d_mask, rg, d_obs, d_ag, d_g);
+        reset_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, d_mask, rg, d_obs, d_ag, d_g, 1);
         return BP_OK;
     });
     if (rc != BP_OK) return rc;
@@ -977,7 +985,44 @@ int bp_step(bp_handle* h, const float* d_actions, int K, float* d_obs, float* d_
     a.actions = d_actions; a.obs = d_obs; a.ag = d_ag; a.reward = d_reward; a.success = d_success; a.done = d_done;
     a.reset_obs = d_reset_obs; a.reset_ag = d_reset_ag; a.actions_out = d_actions_out; a.stats = h->d_stats;
     a.B = h->B; a.stateB = h->B; a.env0 = 0; a.K = K; a.auto_reset = auto_reset; a.rg = ranges_of(h);
+    a.layout = 0; a.k0 = 0; a.Ktot = K; a.goal_out = nullptr;
     return launch_step(h, a, (cudaStream_t)stream);
+}
+
+int bp_rollout(bp_handle* h, const float* d_actions, int test, float* d_o, float* d_ag, float* d_g, float* d_u,
+               float* d_success, float* d_reward, void* stream) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    if (!d_o || !d_ag) return fail(BP_ERR_INVALID_ARG, "bp_rollout needs the o and ag episode tensors");
+    if (step_kernel_choice() != 0) return fail(BP_ERR_INVALID_ARG, "bp_rollout needs the async step kernel");
+    CU(cudaSetDevice(h->device));
+    const int T = BP_MAX_EPISODE_STEPS;
+    Ranges rg = ranges_of(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    // reset_all_rollouts (rollout.py:48-64): reset(), then set_test() for test rollouts; slot 0 of o / ag
+    int rc = dispatch(h->env_id, [&](auto id) {
+        constexpr int ID = decltype(id)::value;
+        reset_kernel<ID><<<nblk(h->B, 128), 128, 0, s>>>(h->d_state, h->B, nullptr, rg, d_o, d_ag, nullptr, T + 1);
+        return (int)BP_OK;
+    });
+    if (rc != BP_OK) return rc;
+    CU(cudaGetLastError());
+    if (test) {
+        if (h->env_id == BP_GRIPPER_TOUCH || h->env_id == BP_TOPPLE_TOWER)
+            return fail(BP_ERR_NOT_IMPLEMENTED, "set_test raises NotImplementedError for this env (fetch_env.py:100-101)");
+        rc = dispatch(h->env_id, [&](auto id) {
+            constexpr int ID = decltype(id)::value;
+            set_test_kernel<ID><<<nblk(h->B, 128), 128, 0, s>>>(h->d_state, h->B, rg, d_o, d_ag, nullptr, T + 1);
+            return (int)BP_OK;
+        });
+        if (rc != BP_OK) return rc;
+        CU(cudaGetLastError());
+    }
+    StepArgs a{};
+    a.actions = d_actions; a.obs = d_o; a.ag = d_ag; a.reward = d_reward; a.success = d_success; a.actions_out = d_u;
+    a.goal_out = d_g; a.stats = h->d_stats;
+    a.B = h->B; a.stateB = h->B; a.env0 = 0; a.K = T; a.auto_reset = 0; a.rg = rg;
+    a.layout = 1; a.k0 = 0; a.Ktot = T;
+    return launch_step(h, a, s);
 }
 
 int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, float* h_ag, float* h_reward,
@@ -1018,6 +1063,7 @@ int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, floa
         a.actions = d_act; a.obs = h_obs ? d_obs : nullptr; a.ag = h_ag ? d_ag : nullptr;
         a.reward = h_reward ? d_r : nullptr; a.success = h_success ? d_s : nullptr;
         a.stats = h->d_stats; a.B = n; a.stateB = h->B; a.env0 = e0; a.K = K; a.auto_reset = auto_reset; a.rg = ranges_of(h);
+        a.layout = 0; a.k0 = 0; a.Ktot = K; a.goal_out = nullptr;
         int rc = launch_step(h, a, s);
         if (rc != BP_OK) return rc;
         if (h_obs) CU(cudaMemcpy2DAsync(h_obs + e0 * dimo, (size_t)h->B * dimo * 4, d_obs, (size_t)n * dimo * 4, (size_t)n * dimo * 4, K, cudaMemcpyDeviceToHost, s));
@@ -1037,7 +1083,7 @@ int bp_set_test(bp_handle* h, float* d_obs, float* d_ag, float* d_g, void* strea
     CU(cudaSetDevice(h->device));
     Ranges rg = ranges_of(h);
     int rc = dispatch(h->env_id, [&](auto id) {
-        set_test_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, rg, d_obs, d_ag, d_g);
+        set_test_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, rg, d_obs, d_ag, d_g, 1);
         return BP_OK;
     });
     if (rc != BP_OK) return rc;

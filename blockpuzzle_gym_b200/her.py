@@ -56,7 +56,7 @@ def make_sample_her_transitions(replay_strategy, replay_k, reward_fun=None, seed
         # the remaining transition keys are plain gathers at (ep_idx, t)
         e, t = out["ep_idx"].long(), out["t"].long()
         for key, val in episode_batch.items():
-            if key in ("g", "ag_2"):
+            if key in ("g", "ag_2", "r"):  # relabelled goal, its reward and ag_2 come from the kernel
                 continue
             if key == "o_2":
                 out[key] = val[e, t]

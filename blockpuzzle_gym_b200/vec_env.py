@@ -206,6 +206,21 @@ class VecBlocksEnv:
         check(self.L.bp_step_host(self._h, C.c_void_p(a_ptr), K, C.c_void_p(obs_ptr), C.c_void_p(ag_ptr),
                                   C.c_void_p(r_ptr), C.c_void_p(s_ptr), int(bool(auto_reset))))
 
+    def generate_rollouts(self, actions=None, test=False):
+        """RolloutStudent.generate_rollouts (rollout.py:75-172) for open-loop actions [T, B, 4] (None: the env's
+        Philox action stream): reset (+ set_test), T = 50 steps, and the episode returned batch-major exactly as
+        convert_episode_to_batch_major (util.py:118-128) lays it out: o [B,T+1,dimo], u [B,T,4], g [B,T,dimg],
+        ag [B,T+1,dimg], info_is_success [B,T,1] (+ r [B,T]).  One reset launch + one fused step launch."""
+        B, T = self.num_envs, MAX_EPISODE_STEPS
+        if actions is not None:
+            actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+            assert actions.shape == (T, B, 4), actions.shape
+        ep = dict(o=self._empty(B, T + 1, self.dimo), u=self._empty(B, T, 4), g=self._empty(B, T, self.dimg),
+                  ag=self._empty(B, T + 1, self.dimg), info_is_success=self._empty(B, T, 1), r=self._empty(B, T))
+        check(self.L.bp_rollout(self._h, _ptr(actions), int(bool(test)), _ptr(ep["o"]), _ptr(ep["ag"]), _ptr(ep["g"]),
+                                _ptr(ep["u"]), _ptr(ep["info_is_success"]), _ptr(ep["r"]), _stream(self.device)))
+        return ep
+
     def goal(self):
         """desired_goal rows [B, dimg]: fixed per env id (colours are fixed lists, fetch_env.py:260-273)."""
         g = _GOALS.get(self.env_id)

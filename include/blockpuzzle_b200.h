@@ -133,6 +133,16 @@ int bp_step(bp_handle* h, const float* d_actions, int K, float* d_obs, float* d_
 int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, float* h_ag,
                  float* h_reward, float* h_success, int auto_reset);
 
+/* RolloutStudent.generate_rollouts (rollout.py:75-172) for open-loop actions, with the per-env loop
+ * (rollout.py:121-131) and convert_episode_to_batch_major (util.py:118-128) fused into the step
+ * kernel: resets every env (plus set_test() when `test`, rollout.py:52-55), runs T = 50 steps on
+ * d_actions [T][B][4] (NULL: in-kernel Philox actions) and writes the episode batch-major:
+ *   d_o [B][T+1][dimo], d_ag [B][T+1][dimg]   (slot 0 = the reset observation)
+ *   d_g [B][T][dimg], d_u [B][T][4], d_success [B][T] (info_is_success), d_reward [B][T]
+ * d_g, d_u, d_success, d_reward may be NULL.  No auto-reset: the episode ends at T. */
+int bp_rollout(bp_handle* h, const float* d_actions, int test, float* d_o, float* d_ag, float* d_g, float* d_u,
+               float* d_success, float* d_reward, void* stream);
+
 /* BlocksTouchEnv.set_test / BlocksTouchChooseEnv.set_test / Variation.set_test
  * (fetch_env.py:365-368, 443-446, 641-644); BP_ERR_NOT_IMPLEMENTED for
  * GripperTouch / ToppleTower (fetch_env.py:100-101). */

@@ -292,3 +292,38 @@ def test_all_step_kernels_agree():
         env = dict(os.environ, BP_STEP_KERNEL=mode, PYTHONPATH=root)
         outs.append(subprocess.check_output([sys.executable, "-c", code], env=env, cwd=root).decode().strip().splitlines()[-1])
     assert outs[0] == outs[1] == outs[2]
+
+
+@pytest.mark.parametrize("name,test", [("BlocksTouch-v0", False), ("BlocksTouchCurriculum-v0", True), ("BlocksTouchVariation-v0", False),
+                                       ("ToppleTower-v0", False)])
+def test_batch_major_rollout_collector(name, test):
+    """generate_rollouts with the env loop and convert_episode_to_batch_major fused.  The oracle
+    follows rollout.py:48-64 + :91-172 step by step; the episode tensors must match bit for bit."""
+    B, T = 300, 50
+    env, ref = _make(name, B, seed=31)
+    rng = np.random.RandomState(8)
+    for episode in range(2):
+        a = rng.uniform(-1, 1, size=(T, B, 4)).astype(np.float32)
+        ep = env.generate_rollouts(torch.from_numpy(a).cuda(), test=test)
+        o0, ag0, g0 = ref.reset()
+        if test:
+            o0, ag0, g0 = ref.set_test()
+        obs, ags, succ, rew = [o0], [ag0], [], []
+        for t in range(T):
+            o, ag, r, s, _, _ = ref.step(a[t])
+            obs.append(o); ags.append(ag); succ.append(s); rew.append(r)
+        swap = lambda x: np.stack(x).swapaxes(0, 1)                      # util.py:118-128
+        assert np.array_equal(ep["o"].cpu().numpy(), swap(obs))
+        assert np.array_equal(ep["ag"].cpu().numpy(), swap(ags))
+        assert np.array_equal(ep["u"].cpu().numpy(), a.swapaxes(0, 1))
+        assert np.array_equal(ep["g"].cpu().numpy(), np.repeat(g0[:, None, :], T, 1))
+        assert np.array_equal(ep["info_is_success"].cpu().numpy()[..., 0], swap(succ))
+        assert np.array_equal(ep["r"].cpu().numpy().view(np.uint32), swap(rew).view(np.uint32))
+        _assert_state_equal(env, ref, f"episode {episode}")
+    # the HER sampler consumes the collector's output directly
+    import blockpuzzle_gym_b200 as bpg
+    tr = bpg.make_sample_her_transitions("future", 4, None, seed=3)(ep, 4096, index_offset=0)
+    ref_tr = coracle.her_relabel(ep["ag"].cpu().numpy(), ep["g"].cpu().numpy(), 4096, 0.8, 3, 0)
+    for k in ("ep_idx", "t", "g", "r"):
+        assert np.array_equal(tr[k].cpu().numpy(), ref_tr[k]), k
+    assert tr["o"].shape == (4096, env.dimo) and tr["u"].shape == (4096, 4)
