@@ -163,6 +163,7 @@ struct StepArgs {
     int k0;
     int Ktot;
     float* goal_out;       // layout 1: desired_goal rows [B][Ktot][DIMG] (nullable)
+    int tune;              // duo kernel: minimum ready lanes for a scheduler iteration while the worker is busy
 };
 
 __device__ __forceinline__ int64_t step_row(const StepArgs& p, int k, int64_t li) {
@@ -806,12 +807,13 @@ static int dispatch(int env_id, F&& f) {
 
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
-// BP_STEP_KERNEL = async (default) | tiled | simple
+// BP_STEP_KERNEL = async (default) | duo | tiled | simple
 static int step_kernel_choice() {
     static const int v = [] {
         const char* e = getenv("BP_STEP_KERNEL");
         if (e && strcmp(e, "simple") == 0) return 2;
         if (e && strcmp(e, "tiled") == 0) return 1;
+        if (e && strcmp(e, "duo") == 0) return 3;
         return 0;
     }();
     return v;
@@ -829,7 +831,7 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
     int rc = dispatch(h->env_id, [&](auto id) {
         constexpr int ID = decltype(id)::value;
         const int choice = step_kernel_choice();
-        if (a.layout != 0 && choice != 0) return fail(BP_ERR_INVALID_ARG, "the batch-major episode layout needs the async step kernel");
+        if (a.layout != 0 && choice != 0 && choice != 3) return fail(BP_ERR_INVALID_ARG, "the batch-major episode layout needs the async / duo step kernel");
         if (choice == 2) {
             constexpr size_t kSmem = sizeof(float) * Col<Cfg<ID>::NB, 128>::kFields * 128;
             step_kernel_simple<ID><<<nblk(a.B, 128), 128, kSmem, s>>>(h->d_state, a);
@@ -850,15 +852,19 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                 static bool attr_set = false;
                 if (!attr_set) {
                     int r = set_smem_attr(step_kernel_async<ID, E>, A::SMEM + pad);
+                    if (r == BP_OK) r = set_smem_attr(step_kernel_duo<ID, E>, Duo<ID, E>::SMEM + pad);
                     if (r != BP_OK) return r;
                     attr_set = true;
                 }
                 // the kernel keeps the reward / success bits of at most kMaxFused steps on chip: split longer K
+                static const int tune = [] { const char* e = getenv("BP_DUO_MIN_READY"); return e ? atoi(e) : 16; }();
                 for (int k0 = 0; k0 < a.K; k0 += kMaxFused) {
                     StepArgs c = a;
+                    c.tune = tune;
                     c.K = (a.K - k0) < kMaxFused ? (a.K - k0) : kMaxFused;
                     c.k0 = a.k0 + k0;
-                    step_kernel_async<ID, E><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
+                    if (choice == 3) step_kernel_duo<ID, E><<<nblk(a.B, A::CS), 64, Duo<ID, E>::SMEM + pad, s>>>(h->d_state, c);
+                    else step_kernel_async<ID, E><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
                 }
                 return (int)BP_OK;
             };

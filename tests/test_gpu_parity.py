@@ -272,8 +272,8 @@ def test_gym_single_env_surface():
 
 def test_all_step_kernels_agree():
     """The quiet path and the schedulers must be result-neutral: BP_STEP_KERNEL=simple runs the full physics
-    for every env-step in order; the warp-autonomous (default) and the tiled kernel must leave byte-identical
-    state and outputs (checked via hashes)."""
+    for every env-step in order; the two-warp (default), the warp-autonomous and the tiled kernel must leave
+    byte-identical state and outputs (checked via hashes)."""
     import hashlib
     import subprocess
     import sys
@@ -288,10 +288,10 @@ def test_all_step_kernels_agree():
         "print(h.hexdigest())\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for mode in ("async", "tiled", "simple"):
+    for mode in ("duo", "async", "tiled", "simple"):
         env = dict(os.environ, BP_STEP_KERNEL=mode, PYTHONPATH=root)
         outs.append(subprocess.check_output([sys.executable, "-c", code], env=env, cwd=root).decode().strip().splitlines()[-1])
-    assert outs[0] == outs[1] == outs[2]
+    assert outs[0] == outs[1] == outs[2] == outs[3]
 
 
 @pytest.mark.parametrize("name,test", [("BlocksTouch-v0", False), ("BlocksTouchCurriculum-v0", True), ("BlocksTouchVariation-v0", False),
