@@ -48,5 +48,17 @@ def make_sample_her_transitions(*a, **kw):
     return _m(*a, **kw)
 
 
+def __getattr__(name):
+    # lazy: ReplayBuffer / Normalizer / update_normalizer (her.py), discounted_returns / trim (pg.py)
+    if name in ("ReplayBuffer", "Normalizer", "update_normalizer"):
+        from . import her
+        return getattr(her, name)
+    if name in ("discounted_returns", "trim"):
+        from . import pg
+        return getattr(pg, name)
+    raise AttributeError(name)
+
+
 __all__ = ["ENV_IDS", "REGISTRY", "BlockPuzzleError", "make", "make_vec", "compute_reward",
-           "register_with_gym", "make_sample_her_transitions"]
+           "register_with_gym", "make_sample_her_transitions", "ReplayBuffer", "Normalizer",
+           "update_normalizer", "discounted_returns", "trim"]

@@ -56,6 +56,11 @@ SYMBOLS = {
     "bp_compute_reward": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "bp_her_relabel": (_i, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _i64, _f, _u64, _i64,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bp_her_sample": (_i, [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _i64, _f, _f, _u64, _i64,
+                           _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bp_moments": (_i, [_vp, _i64, C.c_int32, C.c_int32, C.c_int32, _f, _vp, _vp]),
+    "bp_discounted_returns": (_i, [_vp, _i64, C.c_int32, _vp, _vp, _vp]),
+    "bp_trim": (_i, [_vp, _vp, _vp, _i64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -13,6 +13,7 @@
 
 #include "../../include/blockpuzzle_b200.h"
 #include "bp_device.cuh"
+#include "bp_host.h"
 
 namespace bp {
 
@@ -753,7 +754,8 @@ __global__ void her_relabel_kernel(const float* __restrict__ ep_ag, const float*
 using namespace bp;
 
 static thread_local std::string g_err;
-static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int bp_fail(int code, const std::string& msg) { g_err = msg; return code; }
+static int fail(int code, const std::string& msg) { return bp_fail(code, msg); }
 #define CU(call)                                                                              \
     do {                                                                                      \
         cudaError_t _e = (call);                                                              \

@@ -1,0 +1,328 @@
+// bp_replay.cu -- the callers' data path around the env hot path:
+//
+//   bp_her_sample          ReplayBuffer.sample + _sample_her_transitions [upstream baselines.her] as wired by
+//                          config.py:107-123 and used by ddpg.py:106,168-171,214-222, with _preprocess_og's clip
+//                          (ddpg.py:111-120) and the observation-normaliser sums (ddpg.py:166-190) fused in
+//   bp_moments             Normalizer.update [upstream baselines.her.normalizer], call site ddpg.py:185
+//   bp_discounted_returns  the return accumulation of policy_gradient/rollout.py:255-258
+//   bp_trim                RolloutStudent.trim, policy_gradient/rollout.py:105-171 (batched branch)
+//
+// All four are HBM-bound streaming / gather kernels: rows are moved with 128-bit accesses when the row
+// length allows, a block's threads walk whole output rows in address order (coalesced stores), and the
+// reductions stay in registers / shared memory until one atomic per block and column.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+
+#include "../../include/blockpuzzle_b200.h"
+#include "bp_device.cuh"
+#include "bp_host.h"
+
+namespace bp {
+
+constexpr int kSampleThreads = 256;  // = transitions per block
+
+// np.clip(x, -c, c) (ddpg.py:118-119): NaN passes through like numpy's; c <= 0 disables the clip
+__device__ __forceinline__ float clip_sym(float x, float c) { return c > 0.0f ? (x < -c ? -c : (x > c ? c : x)) : x; }
+
+// Copy rows src[s_off[r]] -> dst[r] for the block's `rows` transitions, V floats per access.  Thread ->
+// (row slot, chunk) is fixed, so a thread always serves the same columns: consecutive threads touch
+// consecutive addresses of a row and consecutive rows of the output.  With STATS the thread keeps the sum
+// and sum of squares of its V columns and adds them to s_acc[2][dim] (shared, double) at the end.
+template <int V, bool STATS>
+__device__ __forceinline__ void gather_rows(const float* __restrict__ src, const int64_t* s_off, float* __restrict__ dst, int dim, int rows,
+                                            float clip, double* s_acc) {
+    const int chunks = dim / V;
+    const int rpi = kSampleThreads / chunks;  // rows per iteration (dim <= 256 floats)
+    const int c = (int)threadIdx.x % chunks, rr = (int)threadIdx.x / chunks;
+    double sum[V], sq[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { sum[j] = 0.0; sq[j] = 0.0; }
+    if (rr < rpi) {
+        for (int r = rr; r < rows; r += rpi) {
+            float v[V];
+            if constexpr (V == 4) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(src + s_off[r]) + c);
+                v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+            } else {
+                v[0] = __ldg(src + s_off[r] + c);
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                v[j] = clip_sym(v[j], clip);
+                if (STATS) { const double d = (double)v[j]; sum[j] += d; sq[j] += d * d; }
+            }
+            if constexpr (V == 4) reinterpret_cast<float4*>(dst + (int64_t)r * dim)[c] = make_float4(v[0], v[1], v[2], v[3]);
+            else dst[(int64_t)r * dim + c] = v[0];
+        }
+        if (STATS) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                atomicAdd(s_acc + c * V + j, sum[j]);
+                atomicAdd(s_acc + dim + c * V + j, sq[j]);
+            }
+        }
+    }
+}
+
+template <bool STATS>
+__device__ __forceinline__ void gather_any(const float* src, const int64_t* s_off, float* dst, int dim, int rows, float clip, double* s_acc) {
+    if (!dst) return;
+    // 128-bit path: rows and the tensors' bases must keep 16-byte alignment
+    if ((dim & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0)
+        gather_rows<4, STATS>(src, s_off, dst, dim, rows, clip, s_acc);
+    else
+        gather_rows<1, STATS>(src, s_off, dst, dim, rows, clip, s_acc);
+}
+
+struct HerSampleArgs {
+    const float *ep_o, *ep_u, *ep_g, *ep_ag, *ep_succ;  // [B][T+1][dimo], [B][T][dimu], [B][T][dimg], [B][T+1][dimg], [B][T]
+    int B, T, dimo, dimu, dimg;
+    int64_t n;
+    float future_p, clip_obs;
+    uint32_t k0, k1;
+    int64_t index_offset;
+    int32_t *ep_idx, *t_idx, *fut_t;
+    float *o, *o2, *u, *g, *ag, *ag2, *r, *succ;
+    double* stats;  // [2 * dimo + 1]: sum, sum of squares of the (clipped) o rows, row count
+};
+
+// One block = 256 transitions.  Phase 1 (thread per transition): the Philox draw -> (episode, t, her,
+// future_t) exactly as bpo_her_relabel / her_relabel_kernel, the reward of (ag_2, relabelled g), the
+// index outputs.  Phase 2 (block-cooperative): the row gathers.
+__global__ void __launch_bounds__(kSampleThreads) her_sample_kernel(const __grid_constant__ HerSampleArgs a) {
+    __shared__ int64_t s_o[kSampleThreads], s_u[kSampleThreads], s_ag[kSampleThreads], s_g[kSampleThreads];
+    __shared__ double s_acc[2 * BP_MAX_DIMO];
+    const int64_t base = (int64_t)blockIdx.x * kSampleThreads;
+    const int rows = (int)((a.n - base) < kSampleThreads ? (a.n - base) : kSampleThreads);
+    const int tid = (int)threadIdx.x;
+    const bool stats = a.stats != nullptr && a.o != nullptr;
+    if (stats)
+        for (int j = tid; j < 2 * a.dimo; j += kSampleThreads) s_acc[j] = 0.0;
+    if (tid < rows) {
+        const int64_t i = base + tid;
+        const uint64_t gi = (uint64_t)(i + a.index_offset);
+        const U4 w = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 3u, 0u, a.k0, a.k1);
+        const int e = (int)__umulhi(w.x, (uint32_t)a.B);           // episode_idxs = randint(0, B)
+        const int t = (int)__umulhi(w.y, (uint32_t)a.T);           // t_samples = randint(T)
+        const bool her = u01(w.z) < a.future_p;                    // uniform(size) < future_p
+        const int off = (int)(u01(w.w) * (float)(a.T - t));        // (uniform * (T - t)).astype(int)
+        const int ft = t + 1 + off;
+        const int64_t ag_off = ((int64_t)e * (a.T + 1) + t) * a.dimg;
+        const int64_t g_off = her ? ((int64_t)e * (a.T + 1) + ft) * a.dimg : ((int64_t)e * a.T + t) * a.dimg;
+        s_o[tid] = ((int64_t)e * (a.T + 1) + t) * a.dimo;
+        s_u[tid] = ((int64_t)e * a.T + t) * a.dimu;
+        s_ag[tid] = ag_off;
+        s_g[tid] = her ? -(g_off + 1) : g_off;                     // negative: the row lives in ep_ag
+        // reward_fun(ag_2, g, info) = compute_reward (config.py:110-111 -> fetch_env.py:135-143)
+        const float* ag2 = a.ep_ag + ag_off + a.dimg;
+        const float* gs = (her ? a.ep_ag : a.ep_g) + g_off;
+        float d = 0.0f;
+        int c = 0;
+        for (int k = 0; k < a.dimg; ++k) {
+            const float x = __ldg(ag2 + k), y = __ldg(gs + k);
+            d = d + x * y;
+            c += (y != 0.0f);
+        }
+        if (a.r) store_reward(a.r + i, d != (float)c);
+        if (a.ep_idx) a.ep_idx[i] = e;
+        if (a.t_idx) a.t_idx[i] = t;
+        if (a.fut_t) a.fut_t[i] = her ? ft : -1;
+        if (a.succ && a.ep_succ) a.succ[i] = __ldg(a.ep_succ + (int64_t)e * a.T + t);
+    }
+    __syncthreads();
+    float* const o = a.o ? a.o + base * a.dimo : nullptr;
+    float* const o2 = a.o2 ? a.o2 + base * a.dimo : nullptr;
+    float* const u = a.u ? a.u + base * a.dimu : nullptr;
+    float* const ag = a.ag ? a.ag + base * a.dimg : nullptr;
+    float* const ag2 = a.ag2 ? a.ag2 + base * a.dimg : nullptr;
+    float* const g = a.g ? a.g + base * a.dimg : nullptr;
+    if (stats) gather_any<true>(a.ep_o, s_o, o, a.dimo, rows, a.clip_obs, s_acc);
+    else gather_any<false>(a.ep_o, s_o, o, a.dimo, rows, a.clip_obs, nullptr);
+    gather_any<false>(a.ep_o + a.dimo, s_o, o2, a.dimo, rows, a.clip_obs, nullptr);          // o_2 = o[:, 1:]
+    if (a.ep_u) gather_any<false>(a.ep_u, s_u, u, a.dimu, rows, 0.0f, nullptr);
+    gather_any<false>(a.ep_ag, s_ag, ag, a.dimg, rows, 0.0f, nullptr);
+    gather_any<false>(a.ep_ag + a.dimg, s_ag, ag2, a.dimg, rows, 0.0f, nullptr);            // ag_2 = ag[:, 1:]
+    if (g) {
+        // the goal row comes from ep_ag (relabelled) or ep_g: resolve per row, then one gather over a common base
+        __syncthreads();
+        const float* lo = a.ep_ag < a.ep_g ? a.ep_ag : a.ep_g;
+        if (tid < rows) {
+            const int64_t v = s_g[tid];
+            s_g[tid] = v < 0 ? (a.ep_ag - lo) + (-v - 1) : (a.ep_g - lo) + v;
+        }
+        __syncthreads();
+        const bool v4 = (a.dimg & 3) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(a.ep_ag) | reinterpret_cast<uintptr_t>(a.ep_g) | reinterpret_cast<uintptr_t>(g)) & 15) == 0;
+        if (v4) gather_rows<4, false>(lo, s_g, g, a.dimg, rows, a.clip_obs, nullptr);
+        else gather_rows<1, false>(lo, s_g, g, a.dimg, rows, a.clip_obs, nullptr);
+    }
+    if (stats) {
+        __syncthreads();
+        for (int j = tid; j < 2 * a.dimo; j += kSampleThreads) atomicAdd(a.stats + j, s_acc[j]);
+        if (tid == 0) atomicAdd(a.stats + 2 * a.dimo, (double)rows);
+    }
+}
+
+// Normalizer.update(v): local_sum += v.sum(0), local_sumsq += (v ** 2).sum(0), local_count += v.shape[0]
+// x [n][dim] (row stride ld, first column col0: the Variation rule o[:, 1:] of ddpg.py:180-181) ->
+// acc [2 * dim + 1] double, added atomically.  Thread = one column of a row slab; block = 256 threads.
+__global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ x, int64_t n, int dim, int ld, int col0, float clip,
+                                                      int rows_per_block, double* acc) {
+    const int cols_per_iter = 256 / dim > 0 ? 256 / dim : 1;  // row slots per block iteration (dim <= 256)
+    const int c = (int)threadIdx.x % dim, rr = (int)threadIdx.x / dim;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+    double s = 0.0, q = 0.0;
+    if (rr < cols_per_iter)
+        for (int64_t r = r0 + rr; r < r1; r += cols_per_iter) {
+            const double d = (double)clip_sym(__ldg(x + r * ld + col0 + c), clip);
+            s += d;
+            q += d * d;
+        }
+    __shared__ double s_acc[2 * 256];
+    for (int j = (int)threadIdx.x; j < 2 * dim; j += 256) s_acc[j] = 0.0;
+    __syncthreads();
+    if (rr < cols_per_iter) { atomicAdd(s_acc + c, s); atomicAdd(s_acc + dim + c, q); }
+    __syncthreads();
+    for (int j = (int)threadIdx.x; j < 2 * dim; j += 256) atomicAdd(acc + j, s_acc[j]);
+    if (threadIdx.x == 0 && r1 > r0) atomicAdd(acc + 2 * dim, (double)(r1 - r0));
+}
+
+// policy_gradient/rollout.py:255-258: after step t, returns[t_] += gamma ** (t - t_) * r_t for t_ < t, with
+// returns[t] = r_t appended first.  So G[t_] = r[t_] + sum_{j >= 1} pw[j] * r[t_ + j], accumulated in that
+// order in float64 (pw[j] = gamma ** j as the host's Python float power).  Thread = one (episode, t_).
+__global__ void discounted_returns_kernel(const float* __restrict__ r, int64_t B, int T, const double* __restrict__ pw, double* __restrict__ G) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    const int64_t b = i / T;
+    const int t0 = (int)(i - b * T);
+    const float* row = r + b * T;
+    double acc = (double)row[t0];
+    for (int t = t0 + 1; t < T; ++t) acc = acc + __dmul_rn(__ldg(pw + (t - t0)), (double)row[t]);
+    G[i] = acc;
+}
+
+// RolloutStudent.trim (policy_gradient/rollout.py:139-171): cut a batch of padded observations / touch
+// matrices down to the `num_objs` objects the expert policy was trained on.  Thread = one output element.
+//   g_, ag_: entries i of the max_objs x max_objs matrix with i // max_objs < num_objs and i % max_objs < num_objs
+//   o_ (Variation, :151-167): columns 1..10, then the 15 base features of every block whose colour one-hot
+//      (argmax of the 4 trailing features, get_color :24-26) is GREEN (2) or BLUE (3), in block order
+//   o_ (otherwise, :169): the first dimo_out columns
+__global__ void trim_kernel(const float* __restrict__ o, const float* __restrict__ g, const float* __restrict__ ag, int64_t n,
+                            int dimo_in, int dimg_in, int dimo_out, int num_objs, int variation,
+                            float* __restrict__ o_out, float* __restrict__ g_out, float* __restrict__ ag_out) {
+    const int dimg_out = num_objs * num_objs;
+    const int per_row = dimo_out + 2 * dimg_out;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * per_row) return;
+    const int64_t row = i / per_row;
+    int c = (int)(i - row * per_row);
+    if (c < dimo_out) {
+        const float* src = o + row * dimo_in;
+        float v;
+        if (!variation) {
+            v = src[c];
+        } else if (c < 10) {                         // ENV_FEATURES after the leading num_blocks scalar
+            v = src[1 + c];
+        } else {
+            const int want = (c - 10) / 15, f = (c - 10) % 15;   // want-th GREEN/BLUE block, feature f
+            const int max_blocks = (dimo_in - 11) / 19;
+            int seen = 0;
+            v = 0.0f;
+            for (int j = 0; j < max_blocks; ++j) {
+                const float* blk = src + 11 + j * 19;
+                int am = 0;                          // np.argmax: first maximum wins
+                float best = blk[15];
+                for (int k = 1; k < 4; ++k)
+                    if (blk[15 + k] > best) { best = blk[15 + k]; am = k; }
+                if (am == 2 || am == 3) {
+                    if (seen == want) { v = blk[f]; break; }
+                    ++seen;
+                }
+            }
+        }
+        if (o_out) o_out[row * dimo_out + c] = v;
+    } else {
+        c -= dimo_out;
+        const bool is_ag = c >= dimg_out;
+        if (is_ag) c -= dimg_out;
+        // the kept entries in increasing i: (a, b) with a, b < num_objs of the max_objs-wide matrix
+        int max_objs = 1;
+        while (max_objs * max_objs < dimg_in) ++max_objs;         // (int)(len(g) ** 0.5)
+        const int src_idx = (c / num_objs) * max_objs + (c % num_objs);
+        if (is_ag) { if (ag_out) ag_out[row * dimg_out + c] = ag[row * dimg_in + src_idx]; }
+        else { if (g_out) g_out[row * dimg_out + c] = g[row * dimg_in + src_idx]; }
+    }
+}
+
+}  // namespace bp
+
+using namespace bp;
+
+extern "C" {
+
+int bp_her_sample(const float* d_ep_o, const float* d_ep_u, const float* d_ep_g, const float* d_ep_ag, const float* d_ep_succ,
+                  int32_t B, int32_t T, int32_t dimo, int32_t dimu, int32_t dimg, int64_t n, float future_p, float clip_obs,
+                  uint64_t seed, int64_t index_offset, int32_t* d_ep_idx, int32_t* d_t, int32_t* d_future_t, float* d_o,
+                  float* d_o2, float* d_u, float* d_g, float* d_ag, float* d_ag2, float* d_r, float* d_succ, double* d_stats,
+                  void* stream) {
+    if (B <= 0 || T <= 0 || dimg <= 0 || dimo <= 0 || n < 0) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes");
+    if (dimo > BP_MAX_DIMO || dimg > 256 || dimu < 0 || dimu > 256) return bp_fail(BP_ERR_INVALID_ARG, "row too long");
+    if (n == 0) return BP_OK;
+    if (!d_ep_ag || !d_ep_g) return bp_fail(BP_ERR_INVALID_ARG, "null episode store");
+    if ((d_o || d_o2) && !d_ep_o) return bp_fail(BP_ERR_INVALID_ARG, "o requested without an observation store");
+    if (d_u && (!d_ep_u || dimu == 0)) return bp_fail(BP_ERR_INVALID_ARG, "u requested without an action store");
+    HerSampleArgs a{};
+    a.ep_o = d_ep_o; a.ep_u = d_ep_u; a.ep_g = d_ep_g; a.ep_ag = d_ep_ag; a.ep_succ = d_ep_succ;
+    a.B = B; a.T = T; a.dimo = dimo; a.dimu = dimu > 0 ? dimu : 1; a.dimg = dimg; a.n = n;
+    a.future_p = future_p; a.clip_obs = clip_obs;
+    a.k0 = (uint32_t)seed; a.k1 = (uint32_t)(seed >> 32); a.index_offset = index_offset;
+    a.ep_idx = d_ep_idx; a.t_idx = d_t; a.fut_t = d_future_t;
+    a.o = d_o; a.o2 = d_o2; a.u = d_u; a.g = d_g; a.ag = d_ag; a.ag2 = d_ag2; a.r = d_r; a.succ = d_succ; a.stats = d_stats;
+    const unsigned blocks = (unsigned)((n + kSampleThreads - 1) / kSampleThreads);
+    her_sample_kernel<<<blocks, kSampleThreads, 0, (cudaStream_t)stream>>>(a);
+    BP_CU(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_moments(const float* d_x, int64_t n, int32_t dim, int32_t ld, int32_t col0, float clip, double* d_acc, void* stream) {
+    if (n < 0 || dim <= 0 || dim > 256 || ld < dim + col0 || col0 < 0) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes");
+    if (n == 0) return BP_OK;
+    if (!d_x || !d_acc) return bp_fail(BP_ERR_INVALID_ARG, "null pointer");
+    // ~8 blocks per SM; every block reduces a contiguous slab of rows
+    int64_t rows_per_block = (n + 148 * 8 - 1) / (148 * 8);
+    if (rows_per_block < 64) rows_per_block = 64;
+    const unsigned blocks = (unsigned)((n + rows_per_block - 1) / rows_per_block);
+    moments_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, n, dim, ld, col0, clip, (int)rows_per_block, d_acc);
+    BP_CU(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_discounted_returns(const float* d_r, int64_t B, int32_t T, const double* d_gamma_pow, double* d_G, void* stream) {
+    if (B < 0 || T <= 0) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes");
+    if (B == 0) return BP_OK;
+    if (!d_r || !d_gamma_pow || !d_G) return bp_fail(BP_ERR_INVALID_ARG, "null pointer");
+    const int64_t n = B * T;
+    discounted_returns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_r, B, T, d_gamma_pow, d_G);
+    BP_CU(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_trim(const float* d_o, const float* d_g, const float* d_ag, int64_t n, int32_t dimo_in, int32_t dimg_in, int32_t dimo_out,
+            int32_t num_objs, int32_t variation, float* d_o_out, float* d_g_out, float* d_ag_out, void* stream) {
+    if (n < 0 || dimo_in <= 0 || dimg_in <= 0 || dimo_out <= 0 || num_objs <= 0) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes");
+    if (num_objs * num_objs > dimg_in || dimo_out > dimo_in) return bp_fail(BP_ERR_INVALID_ARG, "cannot trim to a larger shape");
+    if (variation && (dimo_out != 10 + 15 * (num_objs - 2) || (dimo_in - 11) % 19 != 0))
+        return bp_fail(BP_ERR_INVALID_ARG, "Variation trim needs dimo_out = 10 + 15 * (num_objs - 2) and dimo_in = 11 + 19 * max_blocks");
+    if (n == 0) return BP_OK;
+    if (!d_o || !d_g || !d_ag) return bp_fail(BP_ERR_INVALID_ARG, "null pointer");
+    const int64_t total = n * (dimo_out + 2 * num_objs * num_objs);
+    trim_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_o, d_g, d_ag, n, dimo_in, dimg_in, dimo_out, num_objs,
+                                                                                   variation, d_o_out, d_g_out, d_ag_out);
+    BP_CU(cudaGetLastError());
+    return BP_OK;
+}
+
+}  // extern "C"

@@ -180,6 +180,54 @@ int bp_her_relabel(const float* d_ep_ag, const float* d_ep_g, int32_t B, int32_t
                    int64_t n, float future_p, uint64_t seed, int64_t index_offset, int32_t* d_ep_idx,
                    int32_t* d_t, int32_t* d_future_t, float* d_ag2, float* d_g, float* d_r, void* stream);
 
+/* ---- the callers' data path either side of the env ---- */
+
+/* ReplayBuffer.sample + _sample_her_transitions [upstream baselines.her.replay_buffer / her.her]
+ * as configured by config.py:107-123 and called from ddpg.py:106 (buffer), :168-171 (store_episode,
+ * normaliser statistics) and :214-222 (sample_batch), with DDPG._preprocess_og's clip
+ * (ddpg.py:111-120, clip_obs = 200 config.py:35, relative_goals = False config.py:37) fused in.
+ *   episode store (device): d_ep_o [B][T+1][dimo], d_ep_u [B][T][dimu], d_ep_g [B][T][dimg],
+ *     d_ep_ag [B][T+1][dimg], d_ep_succ [B][T] (info_is_success); d_ep_o / d_ep_u / d_ep_succ may
+ *     be NULL when the matching outputs are NULL.
+ *   Transition i draws Philox block (index_offset + i) of stream 3 under `seed` -- the same draw
+ *   bp_her_relabel uses: episode = randint(B), t = randint(T), relabel when uniform < future_p with
+ *   future_t = t + 1 + int(uniform * (T - t)).
+ *   outputs (any may be NULL): d_ep_idx, d_t, d_future_t int32 [n] (future_t = -1: not relabelled);
+ *     d_o = clip(o[e, t]), d_o2 = clip(o[e, t + 1]) [n][dimo]; d_u [n][dimu]; d_g = clip(relabelled
+ *     goal) [n][dimg] (g_2 of sample_batch is the same tensor); d_ag = ag[e, t], d_ag2 = ag[e, t + 1]
+ *     [n][dimg]; d_r [n] = compute_reward(ag_2, g); d_succ [n].  clip_obs <= 0: no clip (what
+ *     buffer.sample returns before _preprocess_og).
+ *   d_stats (nullable) float64 [2 * dimo + 1]: sum and sum of squares per column of the d_o rows and
+ *     the row count are ADDED to it -- the quantities Normalizer.update accumulates at ddpg.py:185
+ *     (for the Variation env the caller drops column 0, ddpg.py:180-181). */
+int bp_her_sample(const float* d_ep_o, const float* d_ep_u, const float* d_ep_g, const float* d_ep_ag,
+                  const float* d_ep_succ, int32_t B, int32_t T, int32_t dimo, int32_t dimu, int32_t dimg,
+                  int64_t n, float future_p, float clip_obs, uint64_t seed, int64_t index_offset,
+                  int32_t* d_ep_idx, int32_t* d_t, int32_t* d_future_t, float* d_o, float* d_o2, float* d_u,
+                  float* d_g, float* d_ag, float* d_ag2, float* d_r, float* d_succ, double* d_stats,
+                  void* stream);
+
+/* Normalizer.update(v) [upstream baselines.her.normalizer], call site ddpg.py:185: adds
+ * sum_r clip(x[r][col0 + c]), its square and the row count n to d_acc float64 [2 * dim + 1].
+ * x has n rows of stride ld floats (col0 = 1, dim = ld - 1 is the Variation rule of ddpg.py:180-181). */
+int bp_moments(const float* d_x, int64_t n, int32_t dim, int32_t ld, int32_t col0, float clip, double* d_acc,
+               void* stream);
+
+/* policy_gradient/rollout.py:255-258: d_G[b][t] = r[b][t] + sum_{j>=1} gamma_pow[j] * r[b][t + j],
+ * accumulated in increasing j in float64 (gamma_pow[j] = gamma ** j, T doubles on the device;
+ * gamma = 1 - 1/T, policy_gradient/config.py:84).  d_r [B][T] float32, d_G [B][T] float64. */
+int bp_discounted_returns(const float* d_r, int64_t B, int32_t T, const double* d_gamma_pow, double* d_G,
+                          void* stream);
+
+/* RolloutStudent.trim, batched branch (policy_gradient/rollout.py:139-171): cut padded rows down to
+ * the num_objs objects an expert policy was trained on.  d_o [n][dimo_in], d_g / d_ag [n][dimg_in] ->
+ * d_o_out [n][dimo_out], d_g_out / d_ag_out [n][num_objs^2] (outputs nullable).  variation != 0 applies
+ * the BlocksTouchVariation rule (:151-167: drop the block count, keep the GREEN / BLUE blocks' 15 base
+ * features), else o[:, :dimo_out] (:169). */
+int bp_trim(const float* d_o, const float* d_g, const float* d_ag, int64_t n, int32_t dimo_in, int32_t dimg_in,
+            int32_t dimo_out, int32_t num_objs, int32_t variation, float* d_o_out, float* d_g_out, float* d_ag_out,
+            void* stream);
+
 #ifdef __cplusplus
 }
 #endif
