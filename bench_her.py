@@ -69,6 +69,62 @@ def main():
     assert np.array_equal(rr, r.cpu().numpy())
     print(json.dumps({"metric": "compute_reward_rows_per_sec", "impl": "reference numpy formula, 1 core", "value": cpu, "unit": "rows/s"}))
 
+    def line(metric, unit, units, ms, byt, per_key, per, workload):
+        print(json.dumps({"metric": metric, "value": units / (ms * 1e-3), "unit": unit, "ms": ms, "config": {"workload": workload},
+                          "roofline": {"bound": "hbm", "achieved": byt / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": byt / (ms * 1e-3) / 1e9 / peak, per_key: per}}))
+
+    # ---- the full transition sampler (ReplayBuffer.sample + HER + _preprocess_og), with and
+    # without the fused normaliser sums, on a real episode store from the batch-major rollout collector
+    del ag, g, out
+    ep = env.generate_rollouts(None)
+    dimo, dimu = env.dimo, 4
+    sampler = bpg.make_sample_her_transitions("future", 4, None, seed=0, clip_obs=200.0)
+    per = 4 * (2 * (2 * dimo + dimu + 3 * dimg) + 1 + 1 + 1) + 12          # gathered rows in + out, succ in, r + succ out, 3 int32 indices
+    stats = torch.zeros(2 * dimo + 1, dtype=torch.float64, device=dev)
+    keep = {}
+    keep["tr"] = sampler(ep, n, index_offset=0)
+    def run_sampler(with_stats):
+        sampler(ep, n, index_offset=0, stats=stats if with_stats else None, out=keep["tr"])   # staging buffers reused
+    for ws in (False, True):
+        ms = timed(lambda: run_sampler(ws))
+        line("her_sample_transitions_per_sec", "transitions/s", n, ms, n * per, "algorithmic_bytes_per_transition", per,
+             "bp_her_sample: 1Mi full transitions (o,o_2,u,g,ag,ag_2,r,info) from a 20000x50 BlocksTouch-v0 episode store, clip 200, future_p 0.8"
+             + (", normaliser sums fused" if ws else ""))
+    # CPU comparison: the numpy restatement of the upstream sampler on 1 core (bounded sample)
+    from oracle import callers_oracle as co
+    hp = {k: v.cpu().numpy() for k, v in ep.items() if k != "r"}
+    ref_s = co.make_sample_her_transitions("future", 4, lambda ag_2, g, info: co.compute_reward(ag_2, g, info), seed=0)
+    batch = dict(hp, o_2=hp["o"][:, 1:], ag_2=hp["ag"][:, 1:])
+    t0 = time.perf_counter(); ref = ref_s(batch, 1 << 18, index_offset=0); ro, rg = co.preprocess_og(ref["o"], ref["ag"], ref["g"]); dt = time.perf_counter() - t0
+    assert np.array_equal(ro, keep["tr"]["o"][:1 << 18].cpu().numpy()) and np.array_equal(ref["r"], keep["tr"]["r"][:1 << 18].cpu().numpy())
+    print(json.dumps({"metric": "her_sample_transitions_per_sec", "impl": "numpy restatement of the upstream sampler, 1 core, 256Ki transitions", "value": (1 << 18) / dt, "unit": "transitions/s"}))
+
+    # ---- Normalizer.update: column sums of a [1Mi, dimo] matrix
+    x = keep["tr"]["o"]
+    nz = bpg.Normalizer(dimo)
+    ms = timed(lambda: nz.update(x))
+    line("normalizer_rows_per_sec", "rows/s", n, ms, n * dimo * 4, "algorithmic_bytes_per_row", dimo * 4, "bp_moments: sum / sum of squares over [1Mi, 40] float32")
+    xn = x[:1 << 18].cpu().numpy()
+    t0 = time.perf_counter(); xn.sum(axis=0); np.square(xn).sum(axis=0); dt = time.perf_counter() - t0
+    print(json.dumps({"metric": "normalizer_rows_per_sec", "impl": "numpy (upstream Normalizer.update), 1 core, 256Ki rows", "value": (1 << 18) / dt, "unit": "rows/s"}))
+
+    # ---- policy-gradient returns and trim
+    rr = -(torch.rand(n, T, device=dev) < 0.9).float()
+    ms = timed(lambda: bpg.discounted_returns(rr, 1 - 1 / T))   # includes the host-side power table and the output allocation
+    line("discounted_return_episodes_per_sec", "episodes/s", n, ms, n * T * 12, "algorithmic_bytes_per_episode", T * 12, "bp_discounted_returns: 1Mi episodes x T=50, float32 r -> float64 G")
+    t0 = time.perf_counter(); co.discounted_returns(rr[:4096].cpu().numpy().T, 1 - 1 / T); dt = time.perf_counter() - t0
+    print(json.dumps({"metric": "discounted_return_episodes_per_sec", "impl": "reference O(T^2) loop (numpy), 1 core, 4096 episodes", "value": 4096 / dt, "unit": "episodes/s"}))
+    del rr, keep, x, ep
+    venv = bpg.make_vec("BlocksTouchVariation-v0", 1 << 20, device=0, seed=0)
+    o0 = venv.reset()
+    ov, agv, gv = o0["observation"], o0["achieved_goal"], o0["desired_goal"]
+    ms = timed(lambda: bpg.trim(ov, gv, agv, 40, 16, "BlocksTouchVariation-v0"))
+    per = 4 * (87 + 2 * 36 + 40 + 2 * 16)
+    line("trim_rows_per_sec", "rows/s", n, ms, n * per, "algorithmic_bytes_per_row", per, "bp_trim: 1Mi BlocksTouchVariation-v0 rows (87/36/36 -> 40/16/16)")
+    t0 = time.perf_counter(); co.trim(ov[:8192].cpu().numpy(), gv[:8192].cpu().numpy(), agv[:8192].cpu().numpy(), 40, 16, "BlocksTouchVariation-v0"); dt = time.perf_counter() - t0
+    print(json.dumps({"metric": "trim_rows_per_sec", "impl": "reference trim loops (numpy), 1 core, 8192 rows", "value": 8192 / dt, "unit": "rows/s"}))
+
 
 if __name__ == "__main__":
     main()

@@ -22,6 +22,7 @@
 namespace bp {
 
 constexpr int kSampleThreads = 256;  // = transitions per block
+constexpr int kPartials = 2048;       // per-block table of partial column sums (doubles)
 
 // np.clip(x, -c, c) (ddpg.py:118-119): NaN passes through like numpy's; c <= 0 disables the clip
 __device__ __forceinline__ float clip_sym(float x, float c) { return c > 0.0f ? (x < -c ? -c : (x > c ? c : x)) : x; }
@@ -29,7 +30,8 @@ __device__ __forceinline__ float clip_sym(float x, float c) { return c > 0.0f ? 
 // Copy rows src[s_off[r]] -> dst[r] for the block's `rows` transitions, V floats per access.  Thread ->
 // (row slot, chunk) is fixed, so a thread always serves the same columns: consecutive threads touch
 // consecutive addresses of a row and consecutive rows of the output.  With STATS the thread keeps the sum
-// and sum of squares of its V columns and adds them to s_acc[2][dim] (shared, double) at the end.
+// and sum of squares of its V columns and leaves them in s_acc[row slot][2 * dim] (shared, double); the
+// caller adds the row slots up (kPartials doubles cover every dim <= 256: slots * 2 * dim <= 512 * V).
 template <int V, bool STATS>
 __device__ __forceinline__ void gather_rows(const float* __restrict__ src, const int64_t* s_off, float* __restrict__ dst, int dim, int rows,
                                             float clip, double* s_acc) {
@@ -56,11 +58,11 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ src, const
             if constexpr (V == 4) reinterpret_cast<float4*>(dst + (int64_t)r * dim)[c] = make_float4(v[0], v[1], v[2], v[3]);
             else dst[(int64_t)r * dim + c] = v[0];
         }
-        if (STATS) {
+        if (STATS) {  // this thread's partial sums: slot [rr][2 * dim] of the block's table (no atomics)
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                atomicAdd(s_acc + c * V + j, sum[j]);
-                atomicAdd(s_acc + dim + c * V + j, sq[j]);
+                s_acc[rr * 2 * dim + c * V + j] = sum[j];
+                s_acc[rr * 2 * dim + dim + c * V + j] = sq[j];
             }
         }
     }
@@ -93,13 +95,11 @@ struct HerSampleArgs {
 // index outputs.  Phase 2 (block-cooperative): the row gathers.
 __global__ void __launch_bounds__(kSampleThreads) her_sample_kernel(const __grid_constant__ HerSampleArgs a) {
     __shared__ int64_t s_o[kSampleThreads], s_u[kSampleThreads], s_ag[kSampleThreads], s_g[kSampleThreads];
-    __shared__ double s_acc[2 * BP_MAX_DIMO];
+    __shared__ double s_acc[kPartials];
     const int64_t base = (int64_t)blockIdx.x * kSampleThreads;
     const int rows = (int)((a.n - base) < kSampleThreads ? (a.n - base) : kSampleThreads);
     const int tid = (int)threadIdx.x;
     const bool stats = a.stats != nullptr && a.o != nullptr;
-    if (stats)
-        for (int j = tid; j < 2 * a.dimo; j += kSampleThreads) s_acc[j] = 0.0;
     if (tid < rows) {
         const int64_t i = base + tid;
         const uint64_t gi = (uint64_t)(i + a.index_offset);
@@ -160,100 +160,148 @@ __global__ void __launch_bounds__(kSampleThreads) her_sample_kernel(const __grid
     }
     if (stats) {
         __syncthreads();
-        for (int j = tid; j < 2 * a.dimo; j += kSampleThreads) atomicAdd(a.stats + j, s_acc[j]);
+        const bool v4 = (a.dimo & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.ep_o) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
+        const int slots_all = kSampleThreads / (v4 ? a.dimo / 4 : a.dimo);
+        const int slots = slots_all < rows ? slots_all : rows;         // row slots that saw at least one row
+        for (int j = tid; j < 2 * a.dimo; j += kSampleThreads) {
+            double t = 0.0;
+            for (int k = 0; k < slots; ++k) t += s_acc[k * 2 * a.dimo + j];
+            atomicAdd(a.stats + j, t);
+        }
         if (tid == 0) atomicAdd(a.stats + 2 * a.dimo, (double)rows);
     }
 }
 
 // Normalizer.update(v): local_sum += v.sum(0), local_sumsq += (v ** 2).sum(0), local_count += v.shape[0]
 // x [n][dim] (row stride ld, first column col0: the Variation rule o[:, 1:] of ddpg.py:180-181) ->
-// acc [2 * dim + 1] double, added atomically.  Thread = one column of a row slab; block = 256 threads.
+// acc [2 * dim + 1] double, added atomically.  A block of 256 threads walks a slab of rows_per_block rows;
+// a thread always serves the same V columns (V = 4: 128-bit loads when rows keep 16-byte alignment), so its
+// partial sums stay in registers; one shared and one global atomic per column and block at the end.
+template <int V>
 __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ x, int64_t n, int dim, int ld, int col0, float clip,
                                                       int rows_per_block, double* acc) {
-    const int cols_per_iter = 256 / dim > 0 ? 256 / dim : 1;  // row slots per block iteration (dim <= 256)
-    const int c = (int)threadIdx.x % dim, rr = (int)threadIdx.x / dim;
+    const int chunks = dim / V;
+    const int rpi = 256 / chunks;                       // row slots per block iteration (dim <= 256)
+    const int c = (int)threadIdx.x % chunks, rr = (int)threadIdx.x / chunks;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
-    double s = 0.0, q = 0.0;
-    if (rr < cols_per_iter)
-        for (int64_t r = r0 + rr; r < r1; r += cols_per_iter) {
-            const double d = (double)clip_sym(__ldg(x + r * ld + col0 + c), clip);
-            s += d;
-            q += d * d;
+    double s[V], q[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { s[j] = 0.0; q[j] = 0.0; }
+    if (rr < rpi) {
+#pragma unroll 4
+        for (int64_t r = r0 + rr; r < r1; r += rpi) {
+            float v[V];
+            if constexpr (V == 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(x + r * ld + col0) + c);
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            } else {
+                v[0] = __ldg(x + r * ld + col0 + c);
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const double d = (double)clip_sym(v[j], clip);
+                s[j] += d;
+                q[j] += d * d;
+            }
         }
-    __shared__ double s_acc[2 * 256];
-    for (int j = (int)threadIdx.x; j < 2 * dim; j += 256) s_acc[j] = 0.0;
+    }
+    __shared__ double s_part[kPartials];                // [row slot][2 * dim]
+    if (rr < rpi) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { s_part[rr * 2 * dim + c * V + j] = s[j]; s_part[rr * 2 * dim + dim + c * V + j] = q[j]; }
+    }
     __syncthreads();
-    if (rr < cols_per_iter) { atomicAdd(s_acc + c, s); atomicAdd(s_acc + dim + c, q); }
-    __syncthreads();
-    for (int j = (int)threadIdx.x; j < 2 * dim; j += 256) atomicAdd(acc + j, s_acc[j]);
+    for (int j = (int)threadIdx.x; j < 2 * dim; j += 256) {
+        double t = 0.0;
+        for (int k = 0; k < rpi; ++k) t += s_part[k * 2 * dim + j];
+        atomicAdd(acc + j, t);
+    }
     if (threadIdx.x == 0 && r1 > r0) atomicAdd(acc + 2 * dim, (double)(r1 - r0));
 }
 
 // policy_gradient/rollout.py:255-258: after step t, returns[t_] += gamma ** (t - t_) * r_t for t_ < t, with
 // returns[t] = r_t appended first.  So G[t_] = r[t_] + sum_{j >= 1} pw[j] * r[t_ + j], accumulated in that
-// order in float64 (pw[j] = gamma ** j as the host's Python float power).  Thread = one (episode, t_).
-__global__ void discounted_returns_kernel(const float* __restrict__ r, int64_t B, int T, const double* __restrict__ pw, double* __restrict__ G) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * T) return;
-    const int64_t b = i / T;
-    const int t0 = (int)(i - b * T);
-    const float* row = r + b * T;
-    double acc = (double)row[t0];
-    for (int t = t0 + 1; t < T; ++t) acc = acc + __dmul_rn(__ldg(pw + (t - t0)), (double)row[t]);
-    G[i] = acc;
+// order in float64 (pw[j] = gamma ** j as the host's Python float power).  A block stages the rewards of
+// kRetEpisodes episodes and the power table in shared memory (coalesced loads), then every thread produces
+// outputs (episode, t_) in address order (coalesced float64 stores); T <= kRetMaxT.
+constexpr int kRetEpisodes = 32, kRetMaxT = 128;
+__global__ void __launch_bounds__(256) discounted_returns_kernel(const float* __restrict__ r, int64_t B, int T, const double* __restrict__ pw,
+                                                                 double* __restrict__ G) {
+    __shared__ float s_r[kRetEpisodes * kRetMaxT];
+    __shared__ double s_pw[kRetMaxT];
+    const int64_t b0 = (int64_t)blockIdx.x * kRetEpisodes;
+    const int nb = (int)((B - b0) < kRetEpisodes ? (B - b0) : kRetEpisodes);
+    const int total = nb * T;
+    for (int i = (int)threadIdx.x; i < total; i += 256) s_r[i] = __ldg(r + b0 * T + i);
+    for (int i = (int)threadIdx.x; i < T; i += 256) s_pw[i] = pw[i];
+    __syncthreads();
+    for (int i = (int)threadIdx.x; i < total; i += 256) {
+        const int e = i / T, t0 = i - e * T;
+        const float* row = s_r + e * T;
+        double acc = (double)row[t0];
+        for (int t = t0 + 1; t < T; ++t) acc = acc + __dmul_rn(s_pw[t - t0], (double)row[t]);
+        G[b0 * T + i] = acc;
+    }
 }
 
 // RolloutStudent.trim (policy_gradient/rollout.py:139-171): cut a batch of padded observations / touch
-// matrices down to the `num_objs` objects the expert policy was trained on.  Thread = one output element.
+// matrices down to the `num_objs` objects the expert policy was trained on.
 //   g_, ag_: entries i of the max_objs x max_objs matrix with i // max_objs < num_objs and i % max_objs < num_objs
 //   o_ (Variation, :151-167): columns 1..10, then the 15 base features of every block whose colour one-hot
 //      (argmax of the 4 trailing features, get_color :24-26) is GREEN (2) or BLUE (3), in block order
 //   o_ (otherwise, :169): the first dimo_out columns
-__global__ void trim_kernel(const float* __restrict__ o, const float* __restrict__ g, const float* __restrict__ ag, int64_t n,
-                            int dimo_in, int dimg_in, int dimo_out, int num_objs, int variation,
-                            float* __restrict__ o_out, float* __restrict__ g_out, float* __restrict__ ag_out) {
-    const int dimg_out = num_objs * num_objs;
-    const int per_row = dimo_out + 2 * dimg_out;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * per_row) return;
-    const int64_t row = i / per_row;
-    int c = (int)(i - row * per_row);
-    if (c < dimo_out) {
-        const float* src = o + row * dimo_in;
-        float v;
-        if (!variation) {
-            v = src[c];
-        } else if (c < 10) {                         // ENV_FEATURES after the leading num_blocks scalar
-            v = src[1 + c];
-        } else {
-            const int want = (c - 10) / 15, f = (c - 10) % 15;   // want-th GREEN/BLUE block, feature f
-            const int max_blocks = (dimo_in - 11) / 19;
-            int seen = 0;
-            v = 0.0f;
+// A block serves kTrimRows rows: the colour of every (row, block slot) is decided once, the kept slots are
+// listed per row in shared memory, then the block's threads write the three outputs in address order.
+constexpr int kTrimRows = 64, kTrimMaxBlocks = 8;
+__global__ void __launch_bounds__(256) trim_kernel(const float* __restrict__ o, const float* __restrict__ g, const float* __restrict__ ag, int64_t n,
+                                                   int dimo_in, int dimg_in, int dimo_out, int num_objs, int max_objs, int variation,
+                                                   float* __restrict__ o_out, float* __restrict__ g_out, float* __restrict__ ag_out) {
+    __shared__ uint8_t s_keep[kTrimRows][kTrimMaxBlocks];   // [row][k] = k-th kept block slot (0xff: none)
+    const int64_t row0 = (int64_t)blockIdx.x * kTrimRows;
+    const int rows = (int)((n - row0) < kTrimRows ? (n - row0) : kTrimRows);
+    const int tid = (int)threadIdx.x;
+    if (variation) {
+        const int max_blocks = (dimo_in - 11) / 19;
+        if (tid < rows) {
+            const float* src = o + (row0 + tid) * dimo_in;
+            int kept = 0;
             for (int j = 0; j < max_blocks; ++j) {
-                const float* blk = src + 11 + j * 19;
-                int am = 0;                          // np.argmax: first maximum wins
-                float best = blk[15];
+                const float* oh = src + 11 + j * 19 + 15;
+                int am = 0;                                  // np.argmax: the first maximum wins
+                float best = oh[0];
                 for (int k = 1; k < 4; ++k)
-                    if (blk[15 + k] > best) { best = blk[15 + k]; am = k; }
-                if (am == 2 || am == 3) {
-                    if (seen == want) { v = blk[f]; break; }
-                    ++seen;
-                }
+                    if (oh[k] > best) { best = oh[k]; am = k; }
+                if (am == 2 || am == 3) s_keep[tid][kept++] = (uint8_t)j;
             }
+            for (; kept < kTrimMaxBlocks; ++kept) s_keep[tid][kept] = 0xff;
         }
-        if (o_out) o_out[row * dimo_out + c] = v;
-    } else {
-        c -= dimo_out;
-        const bool is_ag = c >= dimg_out;
-        if (is_ag) c -= dimg_out;
-        // the kept entries in increasing i: (a, b) with a, b < num_objs of the max_objs-wide matrix
-        int max_objs = 1;
-        while (max_objs * max_objs < dimg_in) ++max_objs;         // (int)(len(g) ** 0.5)
-        const int src_idx = (c / num_objs) * max_objs + (c % num_objs);
-        if (is_ag) { if (ag_out) ag_out[row * dimg_out + c] = ag[row * dimg_in + src_idx]; }
-        else { if (g_out) g_out[row * dimg_out + c] = g[row * dimg_in + src_idx]; }
+        __syncthreads();
+    }
+    if (o_out) {
+        const int total = rows * dimo_out;
+        for (int i = tid; i < total; i += 256) {
+            const int rr = i / dimo_out, c = i - rr * dimo_out;
+            const float* src = o + (row0 + rr) * dimo_in;
+            float v;
+            if (!variation) {
+                v = src[c];
+            } else if (c < 10) {                             // ENV_FEATURES after the leading num_blocks scalar
+                v = src[1 + c];
+            } else {
+                const int slot = s_keep[rr][(c - 10) / 15];
+                v = slot == 0xff ? 0.0f : src[11 + slot * 19 + (c - 10) % 15];
+            }
+            o_out[row0 * dimo_out + i] = v;
+        }
+    }
+    const int dimg_out = num_objs * num_objs;
+    const int total = rows * dimg_out;
+    for (int i = tid; i < total; i += 256) {
+        const int rr = i / dimg_out, c = i - rr * dimg_out;
+        const int64_t src = (row0 + rr) * dimg_in + (c / num_objs) * max_objs + (c % num_objs);
+        if (g_out) g_out[row0 * dimg_out + i] = g[src];
+        if (ag_out) ag_out[row0 * dimg_out + i] = ag[src];
     }
 }
 
@@ -291,21 +339,22 @@ int bp_moments(const float* d_x, int64_t n, int32_t dim, int32_t ld, int32_t col
     if (n < 0 || dim <= 0 || dim > 256 || ld < dim + col0 || col0 < 0) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes");
     if (n == 0) return BP_OK;
     if (!d_x || !d_acc) return bp_fail(BP_ERR_INVALID_ARG, "null pointer");
-    // ~8 blocks per SM; every block reduces a contiguous slab of rows
+    // 8 resident blocks per SM, one wave; every block reduces a contiguous slab of rows
     int64_t rows_per_block = (n + 148 * 8 - 1) / (148 * 8);
     if (rows_per_block < 64) rows_per_block = 64;
     const unsigned blocks = (unsigned)((n + rows_per_block - 1) / rows_per_block);
-    moments_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, n, dim, ld, col0, clip, (int)rows_per_block, d_acc);
+    const bool v4 = (dim & 3) == 0 && (ld & 3) == 0 && (col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0;
+    if (v4) moments_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, n, dim, ld, col0, clip, (int)rows_per_block, d_acc);
+    else moments_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(d_x, n, dim, ld, col0, clip, (int)rows_per_block, d_acc);
     BP_CU(cudaGetLastError());
     return BP_OK;
 }
 
 int bp_discounted_returns(const float* d_r, int64_t B, int32_t T, const double* d_gamma_pow, double* d_G, void* stream) {
-    if (B < 0 || T <= 0) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes");
+    if (B < 0 || T <= 0 || T > kRetMaxT) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes (T must be in 1..128)");
     if (B == 0) return BP_OK;
     if (!d_r || !d_gamma_pow || !d_G) return bp_fail(BP_ERR_INVALID_ARG, "null pointer");
-    const int64_t n = B * T;
-    discounted_returns_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_r, B, T, d_gamma_pow, d_G);
+    discounted_returns_kernel<<<(unsigned)((B + kRetEpisodes - 1) / kRetEpisodes), 256, 0, (cudaStream_t)stream>>>(d_r, B, T, d_gamma_pow, d_G);
     BP_CU(cudaGetLastError());
     return BP_OK;
 }
@@ -318,9 +367,11 @@ int bp_trim(const float* d_o, const float* d_g, const float* d_ag, int64_t n, in
         return bp_fail(BP_ERR_INVALID_ARG, "Variation trim needs dimo_out = 10 + 15 * (num_objs - 2) and dimo_in = 11 + 19 * max_blocks");
     if (n == 0) return BP_OK;
     if (!d_o || !d_g || !d_ag) return bp_fail(BP_ERR_INVALID_ARG, "null pointer");
-    const int64_t total = n * (dimo_out + 2 * num_objs * num_objs);
-    trim_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_o, d_g, d_ag, n, dimo_in, dimg_in, dimo_out, num_objs,
-                                                                                   variation, d_o_out, d_g_out, d_ag_out);
+    int max_objs = 1;
+    while (max_objs * max_objs < dimg_in) ++max_objs;        // (int)(len(g) ** 0.5), rollout.py:143
+    if (variation && (dimo_in - 11) / 19 > kTrimMaxBlocks) return bp_fail(BP_ERR_INVALID_ARG, "too many block slots");
+    trim_kernel<<<(unsigned)((n + kTrimRows - 1) / kTrimRows), 256, 0, (cudaStream_t)stream>>>(d_o, d_g, d_ag, n, dimo_in, dimg_in, dimo_out, num_objs,
+                                                                                               max_objs, variation, d_o_out, d_g_out, d_ag_out);
     BP_CU(cudaGetLastError());
     return BP_OK;
 }

@@ -57,7 +57,9 @@ def make_sample_her_transitions(replay_strategy, replay_k, reward_fun=None, seed
     state = dict(calls=0)
 
     def _sample_her_transitions(episode_batch, batch_size_in_transitions, index_offset=None, stats=None,
-                                keys=("o", "o_2", "u", "g", "ag", "ag_2", "r", "info_is_success"), clip=None):
+                                keys=("o", "o_2", "u", "g", "ag", "ag_2", "r", "info_is_success"), clip=None, out=None):
+        """out: a dict returned by an earlier call with the same shapes -- its tensors are overwritten
+        instead of allocating new ones (a trainer's staging buffers)."""
         L = _lib.load()
         clip = clip_obs if clip is None else clip
         ag = episode_batch["ag"]
@@ -80,17 +82,20 @@ def make_sample_her_transitions(replay_strategy, replay_k, reward_fun=None, seed
         dev = ag.device
         off = state["calls"] * (1 << 40) if index_offset is None else int(index_offset)
         state["calls"] += 1
-        new = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=dev)
         want = lambda k, have=True: have and k in keys
-        out = dict(ep_idx=new(n, dtype=torch.int32), t=new(n, dtype=torch.int32), future_t=new(n, dtype=torch.int32))
-        if want("o", o is not None): out["o"] = new(n, dimo)
-        if want("o_2", o is not None): out["o_2"] = new(n, dimo)
-        if want("u", u is not None): out["u"] = new(n, dimu)
-        if want("g"): out["g"] = new(n, dimg)
-        if want("ag"): out["ag"] = new(n, dimg)
-        if want("ag_2"): out["ag_2"] = new(n, dimg)
-        if want("r"): out["r"] = new(n)
-        if want("info_is_success", succ is not None): out["info_is_success"] = new(n, 1)
+        if out is None:
+            new = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype, device=dev)
+            out = dict(ep_idx=new(n, dtype=torch.int32), t=new(n, dtype=torch.int32), future_t=new(n, dtype=torch.int32))
+            if want("o", o is not None): out["o"] = new(n, dimo)
+            if want("o_2", o is not None): out["o_2"] = new(n, dimo)
+            if want("u", u is not None): out["u"] = new(n, dimu)
+            if want("g"): out["g"] = new(n, dimg)
+            if want("ag"): out["ag"] = new(n, dimg)
+            if want("ag_2"): out["ag_2"] = new(n, dimg)
+            if want("r"): out["r"] = new(n)
+            if want("info_is_success", succ is not None): out["info_is_success"] = new(n, 1)
+        else:
+            assert out["ep_idx"].shape == (n,) and all(v.is_cuda and v.is_contiguous() for v in out.values())
         if stats is not None:
             assert stats.dtype == torch.float64 and stats.numel() == 2 * dimo + 1 and stats.is_cuda and "o" in out
         check(L.bp_her_sample(_ptr(o), _ptr(u), _ptr(g), _ptr(ag), _ptr(succ), B, T, dimo, dimu, dimg, n,
