@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblockpuzzle_b200.so")
+# BP_LIB_PATH: an alternative build of the same library (A/B measurements of kernel variants on one box)
+LIB_PATH = os.environ.get("BP_LIB_PATH") or os.path.join(_HERE, "libblockpuzzle_b200.so")
 
 ENV_IDS = (
     "GripperTouch-v0",

@@ -231,7 +231,7 @@ void bpo_sim_init(bpo_sim* sim, int env_id) {
 }
 
 static float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
-/* BlockPhys v1.1: the fused multiply-adds of the spec are written explicitly (single rounding) */
+/* BlockPhys v1.1+: the fused multiply-adds of the spec are written explicitly (single rounding) */
 #define F(a, b, c) fmaf((a), (b), (c))
 
 /* fetch_env.py:170-185 + gym.envs.robotics.utils.ctrl_set_action / mocap_set_action
@@ -246,11 +246,15 @@ void bpo_sim_set_action(bpo_sim* sim, const float a[4]) {
     sim->ctrl[1] = clampf(sim->q[1] + ga, 0.0f, CTRL_MAX);
 }
 
+/* first-order rotation of the unit complex number (c, s) by dth, then one Newton step of the inverse
+ * square root at 1 as renormalisation (BlockPhys v1.2): |(c2, s2)|^2 = n2 = 1 + dth^2 up to the previous
+ * step's residue, r = 1.5 - 0.5 n2 = n2^(-1/2) + O((n2 - 1)^2).  The norm stays within 3/8 dth^4 of 1
+ * (< 8e-5 at the 60 rad/s cap) and the iteration is self-correcting; v1.1 used sqrtf and a reciprocal here. */
 static void rot_apply(bpo_block* b, float dth) {
     float c2 = F(-b->s, dth, b->c);
     float s2 = F(b->c, dth, b->s);
-    float n = sqrtf(F(c2, c2, s2 * s2));
-    float r = 1.0f / n;
+    float n2 = F(c2, c2, s2 * s2);
+    float r = F(-0.5f, n2, 1.5f);
     b->c = c2 * r;
     b->s = s2 * r;
 }

@@ -229,7 +229,8 @@ def test_physics_invariants_under_random_actions(name):
         for b in range(4):
             live = nb > b
             cs = st["blk_cs"][live, b]
-            assert np.allclose((cs ** 2).sum(-1), 1.0, atol=1e-6)
+            # BlockPhys v1.2 renormalises with one Newton step: |c^2 + s^2 - 1| <= 3/4 dth^4 <= 1.6e-4 at the 60 rad/s cap
+            assert np.allclose((cs ** 2).sum(-1), 1.0, atol=2e-4)
             assert (st["blk_pos"][live, b, 2] >= 0.025 - 1e-7).all()      # never below the floor
         assert (st["grip_pos"][:, 2] >= 0.4785).all()
         assert (np.abs(st["blk_vel"]) <= 5.0).all() and (np.abs(st["blk_w"]) <= 60.0).all()

@@ -1,0 +1,10 @@
+# usage: bash tools/ab.sh <tag> [libA.so libB.so ...]  -- bench.py on several builds of the library, same box, interleaved twice
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out; tag=$1; shift
+: > gpurun_out/${tag}_ab.log
+for rep in 1 2; do
+for lib in "$@"; do
+  BP_LIB_PATH=$PWD/$lib timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --e2e-steps 1 2>&1 | grep '^{' | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); e=d['episode_stats']; n=d['steps']*8192
+print('$lib', '%.4g'%d['value'], '%.2f ms'%d['ms_per_step'], 'iters/slab %.1f passes/slab %.1f fill %.1f'%(e['sched_iterations']/n, e['sched_passes']/n, e['worker_steps']/max(e['sched_passes'],1)))" >> gpurun_out/${tag}_ab.log
+done; done
+cat gpurun_out/${tag}_ab.log
