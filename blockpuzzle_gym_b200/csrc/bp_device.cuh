@@ -208,9 +208,12 @@ struct Blk { float x, y, z, c, s, vx, vy, vz, w; };
 struct Grip { float g[3], gv[3], q[2], qv[2]; };
 struct GripSub { float gox, goy, qo[2], closed[2]; };
 
-template <int NB, int STRIDE>
+template <int NB, int STRIDE, int SSTRIDE = STRIDE>
 struct Col {
-    float* p;
+    float* p;   // cube fields: field f of cube b at p[(9*b+f)*STRIDE]
+    float* s;   // per-substep scratch: s[(4*b+f)*SSTRIDE] (default: right behind the fields)
+    __device__ __forceinline__ Col(float* fields) : p(fields), s(fields + 9 * NB * STRIDE) {}
+    __device__ __forceinline__ Col(float* fields, float* scratch) : p(fields), s(scratch) {}
     __device__ __forceinline__ Blk load(int b) const {
         const float* q = p + 9 * b * STRIDE;
         return Blk{q[0], q[STRIDE], q[2 * STRIDE], q[3 * STRIDE], q[4 * STRIDE], q[5 * STRIDE], q[6 * STRIDE], q[7 * STRIDE], q[8 * STRIDE]};
@@ -225,12 +228,11 @@ struct Col {
         q[0] = k.x; q[STRIDE] = k.y; q[2 * STRIDE] = k.z; q[3 * STRIDE] = k.c; q[4 * STRIDE] = k.s;
     }
     // scratch: start-of-substep position (0..2) and accumulated yaw change (3)
-    __device__ __forceinline__ float& scr(int b, int f) const { return p[(9 * NB + 4 * b + f) * STRIDE]; }
+    __device__ __forceinline__ float& scr(int b, int f) const { return s[(4 * b + f) * SSTRIDE]; }
     static constexpr int kFields = 13 * NB;
+    static constexpr int kScratch = 4 * NB;
 };
 
-// first-order rotation + one Newton step of rsqrt at 1 as renormalisation (BlockPhys v1.2; v1.1's
-// correctly rounded sqrt + reciprocal were 6.5 % of the step kernel's time, run by 2.3 lanes on average)
 __device__ __forceinline__ void rot_apply(float& c, float& s, float dth) {
     float c2 = F(-s, dth, c);
     float s2 = F(c, dth, s);
@@ -473,8 +475,8 @@ __device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const floa
 
 // the cube part of one substep (steps 3-5 of the spec).  Returns true when the substep left every
 // cube bit-for-bit unchanged (all at rest before and after, nothing moved or rotated): a fixed point.
-template <int NB, int STRIDE>
-__device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB, STRIDE> col, const int nb, uint32_t& contacts) {
+template <int NB, int STRIDE, int SS>
+__device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB, STRIDE, SS> col, const int nb, uint32_t& contacts) {
     uint32_t sup = 0;
     bool rest = true, rotated = false;
     contacts = 0;
@@ -576,8 +578,8 @@ __device__ __forceinline__ void action_targets(const Grip& e, const float a[4], 
 
 // _set_action (fetch_env.py:170-185, after the clip of robot_env.py:58) + sim.step() (robot_env.py:60).
 // Returns whether the cubes ended the step on an exact fixed point; `contacts` = pairs of the last substep.
-template <int NB, int STRIDE, bool BG>
-__device__ __forceinline__ bool sim_step_col(Grip& g, const float a[4], const Col<NB, STRIDE> col, const int nb, uint32_t& contacts) {
+template <int NB, int STRIDE, bool BG, int SS>
+__device__ __forceinline__ bool sim_step_col(Grip& g, const float a[4], const Col<NB, STRIDE, SS> col, const int nb, uint32_t& contacts) {
     float m[3], ctrl[2];
     action_targets<BG>(g, a, m, ctrl);
     bool still = false;
@@ -585,7 +587,7 @@ __device__ __forceinline__ bool sim_step_col(Grip& g, const float a[4], const Co
     for (int sub = 0; sub < kNSub; ++sub) {
         GripSub st;
         substep_gripper<BG>(g, st, m, ctrl);
-        still = substep_cubes<NB, STRIDE>(g, st, col, nb, contacts);
+        still = substep_cubes<NB, STRIDE, SS>(g, st, col, nb, contacts);
     }
     return still;
 }

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128) step_kernel_simple(uint32_t* st, StepArgs
     using C = Cfg<ID>;
     constexpr int NB = C::NB;
     extern __shared__ __align__(16) uint32_t smem[];
-    const Col<NB, 128> col{reinterpret_cast<float*>(smem) + threadIdx.x};
+    const Col<NB, 128> col(reinterpret_cast<float*>(smem) + threadIdx.x);
     int64_t li = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index inside this launch
     const bool live = li < p.B;
     float n_ep = 0.f, n_su = 0.f, n_st = 0.f, n_inv = 0.f, r_sum = 0.f;
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(128, 4) step_kernel_tiled(uint32_t* __restrict
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile0 = (int64_t)blockIdx.x * TILE;  // launch-local index of the tile's env 0
     float* my_stage = s_stage + warp * T::STAGE;
-    const Col<NB, T::THREADS> wcol{s_stage + tid};  // worker column (phase B only; the stage is idle then)
+    const Col<NB, T::THREADS> wcol(s_stage + tid);  // worker column (phase B only; the stage is idle then)
 
     // ---- owner state, 2 envs per thread: slot j owns local env le = j*128 + tid
     Grip gr[EPT];
