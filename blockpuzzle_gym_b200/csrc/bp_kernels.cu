@@ -865,7 +865,9 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                 static const int tune = [choice] {
                     if (choice == 3) { const char* e = getenv("BP_DUO_MIN_READY"); return e ? atoi(e) : 32; }
                     const char* r = getenv("BP_RESET_MIN"); const char* q = getenv("BP_PASS_MIN");
-                    return (r ? atoi(r) : 4) | ((q ? atoi(q) : 32) << 8);   // measured: reset 1/4/8/16/32 -> 3.03/3.08/3.02/2.94/2.99e9; pass 16/24/28/32 -> 2.71/3.01/3.02/3.08e9
+                    const char* fr = getenv("BP_FILL_RULE");   // margin of the fill-comparison pass trigger, -1: off
+                    const int frv = fr ? atoi(fr) : 8;
+                    return (r ? atoi(r) : 4) | ((q ? atoi(q) : 32) << 8) | (frv >= 0 ? (1 << 16) | (frv << 17) : 0);   // measured: reset 1/4/8/16/32 -> 3.03/3.08/3.02/2.94/2.99e9; pass 16/24/28/32 -> 2.71/3.01/3.02/3.08e9
                 }();
                 for (int k0 = 0; k0 < a.K; k0 += kMaxFused) {
                     StepArgs c = a;
