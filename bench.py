@@ -28,7 +28,7 @@ ENV_NAME = "BlocksTouch-v0"
 ENVS_PER_GPU = 1 << 20
 FUSED = 64
 DIMU, DIMO, DIMG = 4, 40, 16
-STATE_BYTES = 35 * 4  # device state words per env (17 + 9 * nblocks) * 4
+STATE_BYTES = 36 * 4  # device state words per env (18 + 9 * nblocks) * 4, bp_create
 # 4*(dimu + dimo + dimg + 2) + 2*state/K bytes per env-step
 BYTES_PER_ENV_STEP = 4 * (DIMU + DIMO + DIMG + 2) + 2.0 * STATE_BYTES / FUSED
 METRIC = "env_steps_per_sec"
@@ -73,16 +73,26 @@ class ClockSampler:
         for line in self.p.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample: brackets the timed region."""
+        return len(self.rows)
+
+    def stop(self, first=0, last=None):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)   # let the sample that covers the end of the timed region arrive
         self.p.terminate()
         try:
             self.p.wait(timeout=2)
         except Exception:
             self.p.kill()
+        last = len(self.rows) if last is None else min(len(self.rows), last + 2)
+        rows = self.rows[first:last]
+        window = "timed region"
+        if not rows:   # region shorter than one sampling period: the samples taken under the warm-up load just before it
+            rows, window = self.rows[max(0, first - 8):first], "warm-up launches right before the timed region"
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -91,7 +101,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------- CPU legs
@@ -199,21 +209,34 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         launch()
         env.stats_reset()
     sync()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # nvidia-smi needs about a second before its first sample: keep the GPU under the same load (untimed
+    # launches, rank 0 decides for all ranks) until the sampler delivers, so that the clocks line describes the
+    # loaded state even when the timed region is shorter than that
+    for _ in range(150):
+        flag = torch.tensor([1 if (rank != 0 or sampler.p is None or sampler.mark() >= 4) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(flag, 0)
+        if int(flag.item()):
+            break
+        launch()
+        env.stats_reset()
+        torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     sync()
+    m0 = sampler.mark()
     ev[0].record()
     for k in range(args.steps):
         launch()
         ev[k + 1].record()
     sync()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(m0, sampler.mark()) if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     kern_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
