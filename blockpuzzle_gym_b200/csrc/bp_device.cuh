@@ -77,7 +77,9 @@ struct Ranges {
 // ---------------------------------------------------------------- Philox + elementary functions
 struct U4 { uint32_t x, y, z, w; };
 
-__device__ __forceinline__ U4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+// out of line (like bp_log / bp_sincos2pi below): the spawn samplers call these from many sites, and the step
+// kernel's speed depends on how much code its resident warps push through the instruction cache
+static __device__ __noinline__ U4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
@@ -91,7 +93,7 @@ __device__ __forceinline__ U4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, 
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 __device__ __forceinline__ float u01_open(uint32_t x) { return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-07f; }
 
-__device__ __forceinline__ float bp_log(float x) {
+static __device__ __noinline__ float bp_log(float x) {
     uint32_t ix = __float_as_uint(x);
     ix += 0x3f800000u - 0x3f3504f3u;
     int e = (int)(ix >> 23) - 127;
@@ -108,7 +110,7 @@ __device__ __forceinline__ float bp_log(float x) {
     return ((s * (hfsq + R) + dk * 9.0580006145e-06f) - hfsq + f) + dk * 6.9313812256e-01f;
 }
 
-__device__ __forceinline__ void bp_sincos2pi(float u, float& sn, float& cs) {
+static __device__ __noinline__ void bp_sincos2pi(float u, float& sn, float& cs) {
     float t = u * 4.0f;
     int k = (int)(t + 0.5f);
     float f = t - (float)k;
