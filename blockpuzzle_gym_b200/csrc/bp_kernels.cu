@@ -681,6 +681,34 @@ __global__ void set_state_kernel(uint32_t* st, int64_t B, const bp_env_state* in
     store_env<C::NB>(st, B, i, e);
 }
 
+// compute_reward for dimg = 4 * CPR with CPR a power of two (16: BlocksTouch): CPR consecutive lanes share a row, each
+// loads ONE float4 of ag and g (a warp reads 512 contiguous bytes per tensor and instruction), and the dot product
+// is accumulated in the reference's left-to-right order by handing the running sum from lane to lane.
+template <int CPR>
+__global__ void __launch_bounds__(256) compute_reward_coop_kernel(const float4* __restrict__ ag, const float4* __restrict__ g, int64_t n,
+                                                                  float* __restrict__ r) {
+    const int64_t total = n * CPR;
+    const int chunk = (int)(threadIdx.x & (CPR - 1));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i - chunk < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = i < total;   // rows never straddle the end: total is a multiple of CPR
+        const float4 x = live ? __ldcs(ag + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 y = live ? __ldcs(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        int c = (y.x != 0.0f) + (y.y != 0.0f) + (y.z != 0.0f) + (y.w != 0.0f);
+        float d = 0.0f;
+#pragma unroll
+        for (int j = 0; j < CPR; ++j) {
+            const float prev = __shfl_up_sync(0xffffffffu, d, 1, CPR);
+            if (chunk == j) {
+                d = j == 0 ? 0.0f : prev;
+                d = d + x.x * y.x; d = d + x.y * y.y; d = d + x.z * y.z; d = d + x.w * y.w;
+            }
+        }
+#pragma unroll
+        for (int o = CPR / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o, CPR);
+        if (live && chunk == CPR - 1) store_reward(r + i / CPR, d != (float)c);
+    }
+}
+
 // BlocksEnv.compute_reward (fetch_env.py:135-143): one thread per row, 128-bit loads when dimg % 4 == 0
 __global__ void compute_reward_kernel(const float* __restrict__ ag, const float* __restrict__ g, int64_t n, int dimg, float* __restrict__ r) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1201,7 +1229,21 @@ int bp_compute_reward(const float* d_ag, const float* d_g, int64_t n, int dimg, 
     if (n < 0 || dimg <= 0) return fail(BP_ERR_INVALID_ARG, "bad n or dimg");
     if (n == 0) return BP_OK;
     if (!d_ag || !d_g || !d_r) return fail(BP_ERR_INVALID_ARG, "null pointer");
-    compute_reward_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(d_ag, d_g, n, dimg, d_r);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_ag) | reinterpret_cast<uintptr_t>(d_g)) & 15) == 0;
+    const int cpr = dimg / 4;
+    if (aligned && (dimg & 3) == 0 && cpr <= 8 && (cpr & (cpr - 1)) == 0) {
+        int64_t blocks = (n * cpr + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;   // grid-stride: a few waves of full blocks
+        const float4* a4 = reinterpret_cast<const float4*>(d_ag);
+        const float4* g4 = reinterpret_cast<const float4*>(d_g);
+        cudaStream_t s = (cudaStream_t)stream;
+        if (cpr == 1) compute_reward_coop_kernel<1><<<(unsigned)blocks, 256, 0, s>>>(a4, g4, n, d_r);
+        else if (cpr == 2) compute_reward_coop_kernel<2><<<(unsigned)blocks, 256, 0, s>>>(a4, g4, n, d_r);
+        else if (cpr == 4) compute_reward_coop_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(a4, g4, n, d_r);
+        else compute_reward_coop_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(a4, g4, n, d_r);
+    } else {
+        compute_reward_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(d_ag, d_g, n, dimg, d_r);
+    }
     CU(cudaGetLastError());
     return BP_OK;
 }
@@ -1212,11 +1254,18 @@ int bp_her_relabel(const float* d_ep_ag, const float* d_ep_g, int32_t B, int32_t
     if (B <= 0 || T <= 0 || dimg <= 0 || n < 0) return fail(BP_ERR_INVALID_ARG, "bad sizes");
     if (n == 0) return BP_OK;
     if (!d_ep_ag || !d_ep_g) return fail(BP_ERR_INVALID_ARG, "null episode store");
-    her_relabel_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(d_ep_ag, d_ep_g, B, T, dimg, n, future_p,
-                                                                      (uint32_t)seed, (uint32_t)(seed >> 32), index_offset,
-                                                                      d_ep_idx, d_t, d_future_t, d_ag2, d_g, d_r);
-    CU(cudaGetLastError());
-    return BP_OK;
+    // the goal / reward subset of the transition sampler: same draw, same kernel (block-cooperative row gathers;
+    // the original thread-per-transition her_relabel_kernel reached 43 % of HBM, BP_HER_RELABEL_LEGACY=1 selects it)
+    static const bool legacy = [] { const char* e = getenv("BP_HER_RELABEL_LEGACY"); return e && atoi(e) != 0; }();
+    if (legacy || dimg > 256) {
+        her_relabel_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(d_ep_ag, d_ep_g, B, T, dimg, n, future_p,
+                                                                          (uint32_t)seed, (uint32_t)(seed >> 32), index_offset,
+                                                                          d_ep_idx, d_t, d_future_t, d_ag2, d_g, d_r);
+        CU(cudaGetLastError());
+        return BP_OK;
+    }
+    return bp_her_sample(nullptr, nullptr, d_ep_g, d_ep_ag, nullptr, B, T, 1, 0, dimg, n, future_p, 0.0f, seed, index_offset,
+                         d_ep_idx, d_t, d_future_t, nullptr, nullptr, nullptr, d_g, nullptr, d_ag2, d_r, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

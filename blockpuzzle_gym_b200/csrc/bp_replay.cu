@@ -42,7 +42,8 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ src, const
 #pragma unroll
     for (int j = 0; j < V; ++j) { sum[j] = 0.0; sq[j] = 0.0; }
     if (rr < rpi) {
-        for (int r = rr; r < rows; r += rpi) {
+#pragma unroll 4
+        for (int r = rr; r < rows; r += rpi) {   // independent rows: several loads in flight per thread
             float v[V];
             if constexpr (V == 4) {
                 const float4 x = __ldg(reinterpret_cast<const float4*>(src + s_off[r]) + c);
@@ -120,10 +121,18 @@ __global__ void __launch_bounds__(kSampleThreads) her_sample_kernel(const __grid
         const float* gs = (her ? a.ep_ag : a.ep_g) + g_off;
         float d = 0.0f;
         int c = 0;
-        for (int k = 0; k < a.dimg; ++k) {
-            const float x = __ldg(ag2 + k), y = __ldg(gs + k);
-            d = d + x * y;
-            c += (y != 0.0f);
+        if ((a.dimg & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.ep_ag) | reinterpret_cast<uintptr_t>(a.ep_g)) & 15) == 0) {
+            for (int k = 0; k < a.dimg / 4; ++k) {   // same left-to-right sum, 128-bit loads
+                const float4 x = __ldg(reinterpret_cast<const float4*>(ag2) + k), y = __ldg(reinterpret_cast<const float4*>(gs) + k);
+                d = d + x.x * y.x; d = d + x.y * y.y; d = d + x.z * y.z; d = d + x.w * y.w;
+                c += (y.x != 0.0f) + (y.y != 0.0f) + (y.z != 0.0f) + (y.w != 0.0f);
+            }
+        } else {
+            for (int k = 0; k < a.dimg; ++k) {
+                const float x = __ldg(ag2 + k), y = __ldg(gs + k);
+                d = d + x * y;
+                c += (y != 0.0f);
+            }
         }
         if (a.r) store_reward(a.r + i, d != (float)c);
         if (a.ep_idx) a.ep_idx[i] = e;
