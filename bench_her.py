@@ -42,6 +42,8 @@ def main():
         ts = []
         for _ in range(reps):
             flush.zero_()
+            torch.cuda._sleep(400000)   # ~0.2 ms of GPU spin: the host enqueues the timed launch before the GPU gets there,
+                                        # so the events bracket device time, not Python / ctypes call latency
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
