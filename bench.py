@@ -35,6 +35,18 @@ METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
 
+
+def _set_env(name):
+    """Rebind the workload constants to another registered env id."""
+    global ENV_NAME, DIMO, DIMG, STATE_BYTES, BYTES_PER_ENV_STEP
+    table = {"GripperTouch-v0": (25, 9, 1), "BlocksTouch-v0": (40, 16, 2), "ToppleTower-v0": (70, 36, 4), "BlocksTouchCurriculum-v0": (40, 16, 2),
+             "BlocksTouchChoose-v0": (55, 25, 3), "BlocksTouchChooseCurriculum-v0": (55, 25, 3), "BlocksTouchVariation-v0": (87, 36, 4)}
+    ENV_NAME = name
+    DIMO, DIMG, nb = table[name]
+    STATE_BYTES = (18 + 9 * nb) * 4
+    BYTES_PER_ENV_STEP = 4 * (DIMU + DIMO + DIMG + 2) + 2.0 * STATE_BYTES / FUSED
+
+
 def _peak_hbm():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -281,7 +293,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[2]: 1Mi batched BlocksTouch-v0 envs per GPU, K=64 fused steps per launch, uniform random actions, auto-reset at T=50",
+            "config": {"workload": ("BASELINE.json configs[2]: " if ENV_NAME == "BlocksTouch-v0" else "per-id table: ") + "1Mi batched %s envs per GPU, K=64 fused steps per launch, uniform random actions, auto-reset at T=50" % ENV_NAME,
                        "env_id": ENV_NAME, "envs_per_gpu": B, "fused_steps_per_launch": K, "env_steps_per_bench_step": world * B * K,
                        "l2": "no flush needed: per-launch inputs (actions %.2f GB) and outputs (%.2f GB) are far larger than the 126 MB L2"
                              % (B * K * 16 / 1e9, B * K * 4 * (DIMO + DIMG + 2) / 1e9),
@@ -317,8 +329,11 @@ def main():
     ap.add_argument("--fused", type=int, default=FUSED)
     ap.add_argument("--e2e-fused", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--env", default=ENV_NAME, help="env id (default: the BASELINE workload BlocksTouch-v0); other ids are parity-suite configs, benched for the per-id table of profiles/README.md")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.env != ENV_NAME:
+        _set_env(args.env)
     if args.impl == "reference":
         run_reference(args)
     else:
