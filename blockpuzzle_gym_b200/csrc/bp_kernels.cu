@@ -877,7 +877,9 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
         } else {
             // envs per lane (tuning).  Measured at the 18 KB slab, resident warps in brackets: E = 2 [20] 2.22e9, 3 [15] 3.16e9,
             // 4 [12] 3.28e9, 5 [10] 3.23e9, 6 [8] 3.08e9 env-steps/s
-            static const int e_sel = [] { const char* e = getenv("BP_ASYNC_E"); return e ? atoi(e) : kAsyncE; }();
+            // per id (E = 4 / 3 / 2): GripperTouch 3.78 / 3.97 / 3.83e9, ToppleTower 1.32 / 1.34 / 1.22e9, Variation 1.42 / 1.46 / 1.41e9
+            static const int e_env = [] { const char* e = getenv("BP_ASYNC_E"); return e ? atoi(e) : 0; }();
+            const int e_sel = e_env ? e_env : ((ID == 0 || ID == 2 || ID == 6) ? 3 : kAsyncE);
             auto go = [&](auto ec) -> int {
                 constexpr int E = decltype(ec)::value;
                 using A = Async<ID, E>;
