@@ -165,6 +165,9 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return x 
 // BlockPhys v1.1: the fused multiply-adds of the spec are written explicitly (the file is compiled
 // with -fmad=false, so nothing else is ever contracted)
 #define F(a, b, c) __fmaf_rn((a), (b), (c))
+#ifndef BP_PACKED_F32X2
+#define BP_PACKED_F32X2 1   // packed f32x2 arithmetic (sm_100+) in the gripper / finger integrators
+#endif
 
 // ---------------------------------------------------------------- env state in registers
 template <int NB>
@@ -444,12 +447,27 @@ __device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const floa
     st.closed[0] = st.closed[1] = 0.0f;
     st.gox = e.g[0]; st.goy = e.g[1];
     st.qo[0] = e.q[0]; st.qo[1] = e.q[1];
+#if BP_PACKED_F32X2
+    {   // x and y as one packed pair: Blackwell's f32x2 instructions are two independent IEEE operations, so the
+        // results are bit-identical to the scalar form (m - g is written as m + (-g): the same rounded value)
+        const float2 d = __fadd2_rn(make_float2(m[0], m[1]), make_float2(-e.g[0], -e.g[1]));
+        const float2 t = __fmul2_rn(make_float2(-kBW, -kBW), make_float2(e.gv[0], e.gv[1]));   // (-b) * v == -(b * v)
+        const float2 acc = __ffma2_rn(make_float2(kKW, kKW), d, t);
+        const float2 gv = __ffma2_rn(acc, make_float2(kH, kH), make_float2(e.gv[0], e.gv[1]));
+        const float2 g = __ffma2_rn(gv, make_float2(kH, kH), make_float2(e.g[0], e.g[1]));
+        e.gv[0] = gv.x; e.gv[1] = gv.y; e.g[0] = g.x; e.g[1] = g.y;
+        const float az = F(kKW, m[2] - e.g[2], -(kBW * e.gv[2]));
+        e.gv[2] = F(az, kH, e.gv[2]);
+        e.g[2] = F(e.gv[2], kH, e.g[2]);
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float acc = F(kKW, m[k] - e.g[k], -(kBW * e.gv[k]));
         e.gv[k] = F(acc, kH, e.gv[k]);
         e.g[k] = F(e.gv[k], kH, e.g[k]);
     }
+#endif
     // the limits below are written as selects (no divergent branches in the 20-substep loop)
     {
         const bool low = e.g[2] < kGZMin;
@@ -457,12 +475,24 @@ __device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const floa
         e.g[2] = low ? kGZMin : e.g[2];
     }
     if (!BG) {
+#if BP_PACKED_F32X2
+        const float2 fd = __fadd2_rn(make_float2(ctrl[0], ctrl[1]), make_float2(-e.q[0], -e.q[1]));
+        const float2 ft = __fmul2_rn(make_float2(-kBF, -kBF), make_float2(e.qv[0], e.qv[1]));
+        const float2 facc = __ffma2_rn(make_float2(kKF, kKF), fd, ft);
+        const float2 fqv = __ffma2_rn(facc, make_float2(kH, kH), make_float2(e.qv[0], e.qv[1]));
+        const float2 fq = __ffma2_rn(fqv, make_float2(kH, kH), make_float2(e.q[0], e.q[1]));
+#endif
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
             const float q_old = e.q[f];
+#if BP_PACKED_F32X2
+            float qv = f == 0 ? fqv.x : fqv.y;
+            float q = f == 0 ? fq.x : fq.y;
+#else
             const float acc = F(kKF, ctrl[f] - e.q[f], -(kBF * e.qv[f]));
             float qv = F(acc, kH, e.qv[f]);
             float q = F(qv, kH, e.q[f]);
+#endif
             const bool low = q < 0.0f;
             qv = (low && qv < 0.0f) ? 0.0f : qv;
             q = low ? 0.0f : q;
