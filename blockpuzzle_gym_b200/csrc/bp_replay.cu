@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/blockpuzzle_b200.h"
@@ -348,8 +349,10 @@ int bp_moments(const float* d_x, int64_t n, int32_t dim, int32_t ld, int32_t col
     if (n < 0 || dim <= 0 || dim > 256 || ld < dim + col0 || col0 < 0) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes");
     if (n == 0) return BP_OK;
     if (!d_x || !d_acc) return bp_fail(BP_ERR_INVALID_ARG, "null pointer");
-    // 8 resident blocks per SM, one wave; every block reduces a contiguous slab of rows
-    int64_t rows_per_block = (n + 148 * 8 - 1) / (148 * 8);
+    // blocks per SM: every block ends with 2 * dim same-address float64 atomics (~7 ns each, serialised), so few fat blocks win:
+    // 4 / 8 / 16 / 32 / 64 per SM -> 61.5 / 67.6 / 71.6 / 77.8 / 133.7 us for [1 Mi, 40]
+    static const int mult = [] { const char* e = getenv("BP_MOMENTS_BLOCKS_PER_SM"); return e ? atoi(e) : 4; }();
+    int64_t rows_per_block = (n + 148 * mult - 1) / (148 * mult);
     if (rows_per_block < 64) rows_per_block = 64;
     const unsigned blocks = (unsigned)((n + rows_per_block - 1) / rows_per_block);
     const bool v4 = (dim & 3) == 0 && (ld & 3) == 0 && (col0 & 3) == 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0;
