@@ -236,6 +236,27 @@ def test_her_relabel_matches_oracle():
             assert int(ft.max()) <= T and int((ft - tr["t"][tr["future_t"] >= 0]).min()) >= 1
 
 
+def test_zero_and_tiny_actions_through_subnormal_velocities():
+    """With (near-)zero actions the gripper velocity decays by 0.8x per substep into the subnormal range and on to
+    zero within ~25 env-steps: the packed f32x2 integrators must keep subnormals exactly like the scalar oracle."""
+    B, K = 96, 45
+    env, ref = _make("BlocksTouch-v0", B, seed=17)
+    env.reset(); ref.reset()
+    a = np.zeros((K, B, 4), np.float32)
+    a[:3] = np.random.RandomState(0).uniform(-1, 1, size=(3, B, 4)).astype(np.float32)   # get it moving first
+    a[3:, B // 2:, :3] = 1e-30                                                          # subnormal-sized targets for half the envs
+    out = env.step_fused(torch.from_numpy(a).cuda(), auto_reset=False)
+    obs = out["observation"].cpu().numpy()
+    tiny = 0
+    for k in range(K):
+        o, ag, r, s, _, _ = ref.step(a[k])
+        assert np.array_equal(obs[k].view(np.uint32), o.view(np.uint32)), k
+        v = np.abs(o[:, 5:8])                                                          # grip_velp * dt
+        tiny += int(((v > 0) & (v < 1.2e-38)).sum())
+    assert tiny > 0, "the test never reached subnormal velocities"
+    _assert_state_equal(env, ref)
+
+
 def test_step_host_matches_device_path():
     import blockpuzzle_gym_b200 as bpg
     B, K = 1000, 7
