@@ -25,6 +25,7 @@ BP_ERR_INVALID_ARG = -1
 BP_ERR_CUDA = -2
 BP_ERR_NOT_IMPLEMENTED = -3
 BP_ERR_NO_DEVICE = -4
+BP_ERR_NO_ATTRIBUTE = -5
 BP_NUM_STATS = 8
 STAT_NAMES = ("episodes", "successes", "steps", "invalid", "reward_sum", "worker_steps", "sched_iterations", "sched_passes")
 STATE_BYTES = 244
@@ -96,6 +97,8 @@ def check(rc):
     msg = load().bp_last_error().decode()
     if rc == BP_ERR_NOT_IMPLEMENTED:
         raise NotImplementedError(msg)
+    if rc == BP_ERR_NO_ATTRIBUTE:
+        raise AttributeError(msg)
     raise BlockPuzzleError(f"blockpuzzle_b200 error {rc}: {msg}")
 
 

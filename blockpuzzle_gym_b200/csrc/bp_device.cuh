@@ -45,9 +45,12 @@ constexpr float kIInv = 2400.0f;
 constexpr float kPosScale = 0.05f;   // fetch_env.py:175
 constexpr float kWsXLo = 1.0f, kWsXHi = 1.6f, kWsYLo = 0.35f, kWsYHi = 1.15f, kWsZHi = 0.9f;
 constexpr float kGrip0X = 1.3419f, kGrip0Y = 0.7491f, kGrip0Z = 0.5347f;
-// spawn geometry, fetch_env.py:19-32
-constexpr float kMinBlockDist = 0.075f;
-constexpr float kTableX = 1.3f, kTableY = 0.75f, kTableW = 0.225f, kTableH = 0.325f;
+// spawn geometry, fetch_env.py:19-32: python floats (binary64), written as the reference's own expressions so that
+// they fold to the same doubles (kTableH = 0.32499999999999996, kMinBlockDist = 0.07500000000000001)
+constexpr double kBlockSize = 0.05;
+constexpr double kMinBlockDist = 1.5 * kBlockSize;
+constexpr double kTableX = 1.05 + 0.25, kTableY = 0.40 + 0.35;
+constexpr double kTableW = 0.25 - kBlockSize / 2, kTableH = 0.35 - kBlockSize / 2;
 constexpr int kMaxSpawnAttempts = 10000;
 constexpr int kT = 50;               // __init__.py:10
 constexpr int kMaxObjs = 6;
@@ -71,7 +74,7 @@ template <> struct Cfg<6> { static constexpr int NB = 4, DIMO = 87, DIMG = 36; s
 
 // curriculum knobs handed to the kernels (host keeps the python doubles, fetch_env.py:340-348,404-415,561-563)
 struct Ranges {
-    float obj_range, max_obj_range, wrong_obj_range;
+    double obj_range, max_obj_range, wrong_obj_range;
 };
 
 // ---------------------------------------------------------------- Philox + elementary functions
@@ -600,9 +603,11 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB
 // mocap target and finger actuator targets from the clipped action (fetch_env.py:170-185)
 template <bool BG>
 __device__ __forceinline__ void action_targets(const Grip& e, const float a[4], float m[3], float ctrl[2]) {
-    m[0] = clampf(F(a[0], kPosScale, e.g[0]), kWsXLo, kWsXHi);
-    m[1] = clampf(F(a[1], kPosScale, e.g[1]), kWsYLo, kWsYHi);
-    m[2] = clampf(F(a[2], kPosScale, e.g[2]), kGZMin, kWsZHi);
+    // v1.3: product and sum rounded separately -- the reference's float32 `pos_ctrl *= 0.05` (fetch_env.py:175)
+    // followed by upstream's float64 mocap_pos + pos_delta narrows to exactly this
+    m[0] = clampf(e.g[0] + a[0] * kPosScale, kWsXLo, kWsXHi);
+    m[1] = clampf(e.g[1] + a[1] * kPosScale, kWsYLo, kWsYHi);
+    m[2] = clampf(e.g[2] + a[2] * kPosScale, kGZMin, kWsZHi);
     float ga = BG ? 0.0f : a[3];
     ctrl[0] = clampf(e.q[0] + ga, 0.0f, kCtrlMax);
     ctrl[1] = clampf(e.q[1] + ga, 0.0f, kCtrlMax);
@@ -654,34 +659,41 @@ __device__ __forceinline__ U4 env_draw(Env<NB>& e, int stream, uint32_t ep) {
     return r;
 }
 
-__device__ __forceinline__ bool out_of_table(float x, float y) {  // fetch_env.py:30-32
-    return fabsf(x - kTableX) > kTableW || fabsf(y - kTableY) > kTableH;
+// The spawn samplers follow the reference's arithmetic operation by operation in binary64 (BlockPhys v1.3): the
+// env's numpy code computes object_xpos in float64 from initial_gripper_xpos (the float64 image of the sim's
+// binary32 grip position), the RandomState draws and python-float ranges; only set_joint_qpos narrows the result
+// into the sim's binary32 qpos.  Rejection tests see the same float64 values as the reference's, so the draw
+// counters cannot drift.  (Resets are one in 50 env-steps and run a warp at a time: the FP64 cost is invisible.)
+__device__ __forceinline__ bool out_of_table(double x, double y) {  // fetch_env.py:30-32
+    return fabs(x - kTableX) > kTableW || fabs(y - kTableY) > kTableH;
 }
-__device__ __forceinline__ float norm2(float x, float y) { return sqrtf(x * x + y * y); }
+// np.linalg.norm of a float64 pair = sqrt(x.dot(x)): numpy's dot accumulates the second product with an fma
+__device__ __forceinline__ double norm2(double x, double y) { return sqrt(__fma_rn(y, y, x * x)); }
+// RandomState.uniform(lo, hi) = lo + (hi - lo) * u on a 24-bit Philox fraction
+__device__ __forceinline__ double uni(double lo, double hi, uint32_t w) { return lo + (hi - lo) * (double)u01(w); }
 
 // direction = normal(2)/|.|, mag = uniform(lo, hi) from the global np.random (stream 1)
 template <int NB>
-__device__ __forceinline__ void sample_around(Env<NB>& e, uint32_t ep, float bx, float by, float lo, float hi, float& x, float& y) {
+__device__ __forceinline__ void sample_around(Env<NB>& e, uint32_t ep, double bx, double by, double lo, double hi, double& x, double& y) {
     U4 r = env_draw(e, 1, ep);
-    float d0, d1;
-    bp_normal2(r.x, r.y, d0, d1);
-    float n = norm2(d0, d1);
+    float z0, z1;
+    bp_normal2(r.x, r.y, z0, z1);
+    double d0 = (double)z0, d1 = (double)z1;
+    double n = norm2(d0, d1);
     d0 = d0 / n; d1 = d1 / n;
     U4 r2 = env_draw(e, 1, ep);
-    float mag = lo + (hi - lo) * u01(r2.x);
+    double mag = uni(lo, hi, r2.x);
     x = bx + d0 * mag;
     y = by + d1 * mag;
 }
 
 template <int NB>
-__device__ __forceinline__ void sample_blue(Env<NB>& e, uint32_t ep, float r, float& x, float& y) {  // fetch_env.py:475-480
-    float half = r / 2.0f;
+__device__ __forceinline__ void sample_blue(Env<NB>& e, uint32_t ep, double r, double& x, double& y) {  // fetch_env.py:475-480
     int it = 0;
     do {
         U4 w = env_draw(e, 0, ep);
-        float lo = -half;
-        x = kGrip0X + (lo + (half - lo) * u01(w.x));
-        y = kGrip0Y + (lo + (half - lo) * u01(w.y));
+        x = (double)kGrip0X + uni(-r / 2, r / 2, w.x);
+        y = (double)kGrip0Y + uni(-r / 2, r / 2, w.y);
     } while (out_of_table(x, y) && ++it < kMaxSpawnAttempts);
 }
 
@@ -689,44 +701,42 @@ __device__ __forceinline__ void sample_blue(Env<NB>& e, uint32_t ep, float r, fl
 template <int ID>
 __device__ __forceinline__ void randomize_objects(Env<Cfg<ID>::NB>& e, uint32_t ep, bool test, const Ranges& rg) {
     constexpr int NB = Cfg<ID>::NB;
+    const double g0x = (double)kGrip0X, g0y = (double)kGrip0Y;   // initial_gripper_xpos[:2]
     if (ID == 0 || ID == 2) {  // GripperTouch fetch_env.py:328-336, ToppleTower :777-787
-        float r = rg.obj_range;
-        float x = kGrip0X, y = kGrip0Y;
+        double r = rg.obj_range;
+        double x = g0x, y = g0y;
         int it = 0;
-        while (norm2(x - kGrip0X, y - kGrip0Y) < 0.1f && it++ < kMaxSpawnAttempts) {
+        while (norm2(x - g0x, y - g0y) < 0.1 && it++ < kMaxSpawnAttempts) {
             U4 w = env_draw(e, 0, ep);
-            float lo = -r;
-            x = kGrip0X + (lo + (r - lo) * u01(w.x));
-            y = kGrip0Y + (lo + (r - lo) * u01(w.y));
+            x = g0x + uni(-r, r, w.x);
+            y = g0y + uni(-r, r, w.y);
         }
 #pragma unroll
-        for (int i = 0; i < NB; ++i) { e.px[i] = x; e.py[i] = y; }
+        for (int i = 0; i < NB; ++i) { e.px[i] = (float)x; e.py[i] = (float)y; }
     } else if (ID == 1 || ID == 3) {  // BlocksTouch fetch_env.py:370-399
-        float r = test ? rg.max_obj_range : rg.obj_range;
-        float half = r / 2.0f;
+        double r = test ? rg.max_obj_range : rg.obj_range;
         U4 w = env_draw(e, 0, ep);
-        float lo = -half;
-        float x0 = kGrip0X + (lo + (half - lo) * u01(w.x));
-        float y0 = kGrip0Y + (lo + (half - lo) * u01(w.y));
-        e.px[0] = x0; e.py[0] = y0;
-        float x, y;
+        double x0 = g0x + uni(-r / 2, r / 2, w.x);
+        double y0 = g0y + uni(-r / 2, r / 2, w.y);
+        e.px[0] = (float)x0; e.py[0] = (float)y0;
+        double x, y;
         int it = 0;
         do {
             sample_around(e, ep, x0, y0, kMinBlockDist, r, x, y);
         } while (out_of_table(x, y) && ++it < kMaxSpawnAttempts);
-        if (NB > 1) { e.px[NB > 1 ? 1 : 0] = x; e.py[NB > 1 ? 1 : 0] = y; }
+        if (NB > 1) { e.px[NB > 1 ? 1 : 0] = (float)x; e.py[NB > 1 ? 1 : 0] = (float)y; }
     } else if (ID == 4 || ID == 5) {  // BlocksTouchChoose fetch_env.py:448-517 (challenge=False)
-        float r, wrong_r;
-        if (test) { r = rg.max_obj_range; wrong_r = 0.0f; }
+        double r, wrong_r;
+        if (test) { r = rg.max_obj_range; wrong_r = 0.0; }
         else { r = rg.obj_range; wrong_r = rg.wrong_obj_range; }
-        float max_wrong_r = rg.max_obj_range;
-        float bx, by, gx, gy, wx, wy;
+        double max_wrong_r = rg.max_obj_range;
+        double bx, by, gx, gy, wx, wy;
         sample_blue(e, ep, r, bx, by);
         int it = 0;
         do {
             sample_around(e, ep, bx, by, kMinBlockDist, r, gx, gy);
         } while (out_of_table(gx, gy) && ++it < kMaxSpawnAttempts);
-        float cx = (bx + gx) / 2.0f, cy = (by + gy) / 2.0f;
+        double cx = (bx + gx) / 2.0, cy = (by + gy) / 2.0;
         it = 0;
         bool again;
         do {
@@ -735,42 +745,40 @@ __device__ __forceinline__ void randomize_objects(Env<Cfg<ID>::NB>& e, uint32_t 
         } while (again && ++it < kMaxSpawnAttempts);
         // colours [GREEN, BLUE, GREY]: green = 0, blue = 1, wrong = 2 (fetch_env.py:465-473)
         constexpr int iG = 0, iB = NB > 1 ? 1 : 0, iW = NB > 2 ? 2 : 0;
-        e.px[iB] = bx; e.py[iB] = by;
-        e.px[iG] = gx; e.py[iG] = gy;
-        e.px[iW] = wx; e.py[iW] = wy;
+        e.px[iB] = (float)bx; e.py[iB] = (float)by;
+        e.px[iG] = (float)gx; e.py[iG] = (float)gy;
+        e.px[iW] = (float)wx; e.py[iW] = (float)wy;
     } else {  // BlocksTouchVariation fetch_env.py:697-764
-        float r = test ? rg.max_obj_range : rg.obj_range;
-        float ppx[4], ppy[4];
-        float bx, by, gx, gy;
+        double r = test ? rg.max_obj_range : rg.obj_range;
+        double ppx[4], ppy[4];
+        double bx, by, gx, gy;
         sample_blue(e, ep, r, bx, by);
         int it = 0;
         do {
             sample_around(e, ep, bx, by, kMinBlockDist, r, gx, gy);
         } while (out_of_table(gx, gy) && ++it < kMaxSpawnAttempts);
         constexpr int iG = 0, iB = NB > 1 ? 1 : 0;
-        e.px[iB] = bx; e.py[iB] = by;
-        e.px[iG] = gx; e.py[iG] = gy;
+        e.px[iB] = (float)bx; e.py[iB] = (float)by;
+        e.px[iG] = (float)gx; e.py[iG] = (float)gy;
         ppx[0] = bx; ppy[0] = by; ppx[1] = gx; ppy[1] = gy;
 #pragma unroll
         for (int i = 2; i < NB; ++i) {
             if (i < e.nb) {
-                float x, y;
+                double x, y;
                 bool again;
                 it = 0;
                 do {
                     U4 wa = env_draw(e, 0, ep);  // _sample_from_table fetch_env.py:88-90
                     U4 wb = env_draw(e, 0, ep);
-                    float ux = -kTableW + (kTableW - (-kTableW)) * u01(wa.x);
-                    float uy = -kTableH + (kTableH - (-kTableH)) * u01(wb.x);
-                    x = kTableX + ux;
-                    y = kTableY + uy;
+                    x = kTableX + uni(-kTableW, kTableW, wa.x);
+                    y = kTableY + uni(-kTableH, kTableH, wb.x);
                     bool hit = false;
 #pragma unroll
                     for (int p = 0; p < 4; ++p)
                         if (p < i && !hit && norm2(x - ppx[p], y - ppy[p]) < kMinBlockDist) hit = true;
                     again = hit ? true : out_of_table(x, y);
                 } while (again && ++it < kMaxSpawnAttempts);
-                e.px[i] = x; e.py[i] = y;
+                e.px[i] = (float)x; e.py[i] = (float)y;
                 ppx[i] = x; ppy[i] = y;
             }
         }
@@ -870,7 +878,7 @@ __device__ __forceinline__ void env_write_obs(const Env<Cfg<ID>::NB>& e, Store&&
         put(o + 3, live ? e.px[i] - e.g[0] : 0.0f);
         put(o + 4, live ? e.py[i] - e.g[1] : 0.0f);
         put(o + 5, live ? e.pz[i] - e.g[2] : 0.0f);
-        put(o + 6, 0.0f);
+        put(o + 6, live ? __uint_as_float(0x80000000u) : 0.0f);   // roll: mat2euler gives -arctan2(0, 1) = -0.0 (fetch_env.py:205)
         put(o + 7, 0.0f);
         put(o + 8, live ? bp_atan2(e.s[i], e.c[i]) : 0.0f);
         put(o + 9, live ? e.vx[i] * kDt - gvp0 : 0.0f);

@@ -818,7 +818,7 @@ struct bp_handle {
 };
 
 static Ranges ranges_of(const bp_handle* h) {
-    return Ranges{(float)h->obj_range, (float)h->max_obj_range, (float)h->wrong_obj_range};
+    return Ranges{h->obj_range, h->max_obj_range, h->wrong_obj_range};
 }
 
 template <typename F>
@@ -1151,7 +1151,7 @@ int bp_increase_difficulty(bp_handle* h, int* max_reached) {
             break;
         case BP_BLOCKS_TOUCH_CHOOSE:
         case BP_BLOCKS_TOUCH_CHOOSE_CURRICULUM:  // fetch_env.py:419-432
-            if (!h->has_step) return fail(BP_ERR_NOT_IMPLEMENTED, "AttributeError: no obj_range_step (fetch_env.py:413-415,420)");
+            if (!h->has_step) return fail(BP_ERR_NO_ATTRIBUTE, "'BlocksTouchChooseEnv' object has no attribute 'obj_range_step' (fetch_env.py:413-415,420)");
             h->obj_range += h->obj_range_step;
             h->wrong_obj_range -= h->wrong_obj_range_step;
             if (h->obj_range > h->max_obj_range) {

@@ -31,8 +31,9 @@ typedef enum {
     BP_OK = 0,
     BP_ERR_INVALID_ARG = -1,
     BP_ERR_CUDA = -2,
-    BP_ERR_NOT_IMPLEMENTED = -3, /* the reference method raises NotImplementedError / AttributeError */
-    BP_ERR_NO_DEVICE = -4
+    BP_ERR_NOT_IMPLEMENTED = -3, /* the reference method raises NotImplementedError */
+    BP_ERR_NO_DEVICE = -4,
+    BP_ERR_NO_ATTRIBUTE = -5     /* the reference method raises AttributeError (fetch_env.py:413-415,420) */
 } bp_status;
 
 /* env ids in the registration order of __init__.py:6-53 */
@@ -149,7 +150,9 @@ int bp_rollout(bp_handle* h, const float* d_actions, int test, float* d_o, float
 int bp_set_test(bp_handle* h, float* d_obs, float* d_ag, float* d_g, void* stream);
 
 /* increase_difficulty (fetch_env.py:351-358, 419-432, 623-630): *max_reached
- * receives the python return value; BP_ERR_NOT_IMPLEMENTED where the reference raises. */
+ * receives the python return value; BP_ERR_NOT_IMPLEMENTED where the reference raises NotImplementedError
+ * (GripperTouch, ToppleTower: fetch_env.py:93-94), BP_ERR_NO_ATTRIBUTE where it raises AttributeError
+ * (BlocksTouchChoose-v0 without curriculum: obj_range_step is never set, fetch_env.py:413-415,420). */
 int bp_increase_difficulty(bp_handle* h, int* max_reached);
 int bp_get_difficulty(const bp_handle* h, int* difficulty);           /* fetch_env.py:96-97 */
 /* direct access to the curriculum knobs (obj_range, wrong_obj_range, max_obj_range) */

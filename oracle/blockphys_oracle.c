@@ -67,13 +67,16 @@
 #define GRIP0_Y 0.7491f
 #define GRIP0_Z 0.5347f
 
-/* spawn geometry, fetch_env.py:19-32 */
-#define MIN_BLOCK_DIST 0.075f /* 1.5 * BLOCK_SIZE */
-#define TABLE_X 1.3f          /* 1.05 + 0.25 */
-#define TABLE_Y 0.75f         /* 0.40 + 0.35 */
-#define TABLE_W 0.225f        /* 0.25 - BLOCK_SIZE/2 */
-#define TABLE_H 0.325f        /* 0.35 - BLOCK_SIZE/2 */
-#define MAX_SPAWN_ATTEMPTS 10000
+/* spawn geometry, fetch_env.py:19-32: python floats (binary64), written as the reference's own
+ * expressions so that the compiler folds them to the same doubles (TABLE_H is 0.32499999999999996,
+ * MIN_BLOCK_DIST 0.07500000000000001); tests/test_ref_pin.py compares their bits with the module's. */
+#define BLOCK_SIZE 0.05
+#define MIN_BLOCK_DIST (1.5 * BLOCK_SIZE)
+#define TABLE_X (1.05 + 0.25)
+#define TABLE_Y (0.40 + 0.35)
+#define TABLE_W (0.25 - BLOCK_SIZE / 2)
+#define TABLE_H (0.35 - BLOCK_SIZE / 2)
+#define MAX_SPAWN_ATTEMPTS 10000 /* BlockPhys cap; the reference loops without bound */
 
 static const int k_nblocks[BPO_NUM_ENV_IDS] = {1, 2, 4, 2, 3, 3, 4};
 static const int k_dimo[BPO_NUM_ENV_IDS] = {25, 40, 70, 40, 55, 55, 87};
@@ -234,13 +237,26 @@ static float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi 
 /* BlockPhys v1.1+: the fused multiply-adds of the spec are written explicitly (single rounding) */
 #define F(a, b, c) fmaf((a), (b), (c))
 
+/* What MuJoCo is handed by gym.envs.robotics.utils.mocap_set_action / ctrl_set_action [upstream]:
+ * mocap_pos and the two finger-actuator controls as float64.  BlockPhys narrows them to binary32,
+ * keeps the mocap target inside the arm-reach box and the controls inside ctrlrange (2blocks.xml:40). */
+void bpo_sim_set_targets(bpo_sim* sim, const double mocap_pos[3], const double ctrl[2]) {
+    sim->m[0] = clampf((float)mocap_pos[0], WS_XLO, WS_XHI);
+    sim->m[1] = clampf((float)mocap_pos[1], WS_YLO, WS_YHI);
+    sim->m[2] = clampf((float)mocap_pos[2], GZ_MIN, WS_ZHI);
+    sim->ctrl[0] = clampf((float)ctrl[0], 0.0f, CTRL_MAX);
+    sim->ctrl[1] = clampf((float)ctrl[1], 0.0f, CTRL_MAX);
+}
+
 /* fetch_env.py:170-185 + gym.envs.robotics.utils.ctrl_set_action / mocap_set_action
- * [upstream, recalled]: mocap is snapped to the welded body, then moved by
- * 0.05*a[:3]; finger position-actuator target = qpos + a[3], clipped to ctrlrange. */
+ * [upstream, recalled]: pos_ctrl = a[:3] * 0.05 in the action's float32 (:175), the mocap is
+ * snapped to the welded body and moved by pos_ctrl; finger position-actuator target = qpos + a[3].
+ * v1.3: the product and the sum are rounded separately, which is what the reference's float32
+ * multiply followed by the float64 mocap_pos + pos_delta narrows to (v1.1-1.2 fused them). */
 void bpo_sim_set_action(bpo_sim* sim, const float a[4]) {
-    sim->m[0] = clampf(F(a[0], POS_SCALE, sim->g[0]), WS_XLO, WS_XHI);
-    sim->m[1] = clampf(F(a[1], POS_SCALE, sim->g[1]), WS_YLO, WS_YHI);
-    sim->m[2] = clampf(F(a[2], POS_SCALE, sim->g[2]), GZ_MIN, WS_ZHI);
+    sim->m[0] = clampf(sim->g[0] + a[0] * POS_SCALE, WS_XLO, WS_XHI);
+    sim->m[1] = clampf(sim->g[1] + a[1] * POS_SCALE, WS_YLO, WS_YHI);
+    sim->m[2] = clampf(sim->g[2] + a[2] * POS_SCALE, GZ_MIN, WS_ZHI);
     float ga = sim->block_gripper ? 0.0f : a[3]; /* fetch_env.py:179-180 */
     sim->ctrl[0] = clampf(sim->q[0] + ga, 0.0f, CTRL_MAX);
     sim->ctrl[1] = clampf(sim->q[1] + ga, 0.0f, CTRL_MAX);
@@ -639,24 +655,31 @@ static void env_draw(bpo_env* env, int stream, uint32_t out[4]) {
     env->draws[stream] += 1;
 }
 
-/* self.np_random.uniform(lo, hi, size=2) */
-static void rs_uniform2(bpo_env* env, int stream, float lo, float hi, float* a, float* b) {
+/* The spawn samplers follow the reference's arithmetic operation by operation in binary64 (v1.3):
+ * the env's python/numpy code computes object_xpos in float64 from initial_gripper_xpos (the float64
+ * image of the sim's binary32 grip position), the RandomState draws and python-float ranges, and only
+ * set_joint_qpos narrows the result into the sim's binary32 qpos.  Rejection tests therefore see the
+ * same float64 values as the reference's, and the draw counters cannot drift.
+ * RandomState.uniform(low, high) is low + (high - low) * u, u = 24-bit Philox fraction (exact). */
+static void rs_uniform2(bpo_env* env, int stream, double lo, double hi, double* a, double* b) {
     uint32_t w[4];
     env_draw(env, stream, w);
-    *a = lo + (hi - lo) * bpo_u01(w[0]);
-    *b = lo + (hi - lo) * bpo_u01(w[1]);
+    *a = lo + (hi - lo) * (double)bpo_u01(w[0]);
+    *b = lo + (hi - lo) * (double)bpo_u01(w[1]);
 }
 /* uniform(lo, hi) scalar */
-static float rs_uniform1(bpo_env* env, int stream, float lo, float hi) {
+static double rs_uniform1(bpo_env* env, int stream, double lo, double hi) {
     uint32_t w[4];
     env_draw(env, stream, w);
-    return lo + (hi - lo) * bpo_u01(w[0]);
+    return lo + (hi - lo) * (double)bpo_u01(w[0]);
 }
-/* np.random.normal(size=2) */
-static void rs_normal2(bpo_env* env, int stream, float* a, float* b) {
+/* np.random.normal(size=2): the spec'd binary32 Box-Muller pair, widened */
+static void rs_normal2(bpo_env* env, int stream, double* a, double* b) {
     uint32_t w[4];
+    float z0, z1;
     env_draw(env, stream, w);
-    bpo_normal2(w[0], w[1], a, b);
+    bpo_normal2(w[0], w[1], &z0, &z1);
+    *a = (double)z0; *b = (double)z1;
 }
 /* np_random.randint(n) */
 static int rs_randint(bpo_env* env, int stream, int n) {
@@ -665,51 +688,54 @@ static int rs_randint(bpo_env* env, int stream, int n) {
     return (int)(((uint64_t)w[0] * (uint64_t)n) >> 32);
 }
 
-static int out_of_table(float x, float y) { /* fetch_env.py:30-32 */
-    return fabsf(x - TABLE_X) > TABLE_W || fabsf(y - TABLE_Y) > TABLE_H;
+static int out_of_table(double x, double y) { /* fetch_env.py:30-32 */
+    return fabs(x - TABLE_X) > TABLE_W || fabs(y - TABLE_Y) > TABLE_H;
 }
-static float norm2(float x, float y) { return sqrtf(x * x + y * y); } /* np.linalg.norm */
+/* np.linalg.norm of a float64 2-vector = sqrt(x.dot(x)); numpy's dot accumulates the second product
+ * with a fused multiply-add (checked against numpy 2.3 in tests/test_ref_pin.py) */
+static double norm2(double x, double y) { return sqrt(fma(y, y, x * x)); }
 
-static void set_block_xy(bpo_env* env, int i, float x, float y) { /* object_qpos[:2] = object_xpos */
-    env->sim.blk[i].pos[0] = x;
-    env->sim.blk[i].pos[1] = y;
+static void set_block_xy(bpo_env* env, int i, double x, double y) { /* object_qpos[:2] = object_xpos; set_joint_qpos */
+    env->sim.blk[i].pos[0] = (float)x;
+    env->sim.blk[i].pos[1] = (float)y;
 }
 
 /* direction = normal(2)/|.|; mag = uniform(lo, hi); xy = base + direction*mag
  * (fetch_env.py:390-393, 490-493, 507-510, 734-737); draws from the GLOBAL np.random -> stream 1 */
-static void sample_around(bpo_env* env, float bx, float by, float lo, float hi, float* x, float* y) {
-    float d0, d1;
+static void sample_around(bpo_env* env, double bx, double by, double lo, double hi, double* x, double* y) {
+    double d0, d1;
     rs_normal2(env, 1, &d0, &d1);
-    float n = norm2(d0, d1);
+    double n = norm2(d0, d1);
     d0 = d0 / n; d1 = d1 / n;
-    float mag = rs_uniform1(env, 1, lo, hi);
+    double mag = rs_uniform1(env, 1, lo, hi);
     *x = bx + d0 * mag;
     *y = by + d1 * mag;
 }
 
 /* GripperTouchEnv._randomize_objects fetch_env.py:328-336; ToppleTowerEnv :777-787 */
 static void randomize_gripper_touch(bpo_env* env, int nset) {
-    float r = (float)env->obj_range;
-    float x = GRIP0_X, y = GRIP0_Y;
+    const double g0x = (double)GRIP0_X, g0y = (double)GRIP0_Y; /* initial_gripper_xpos[:2] */
+    double r = env->obj_range;
+    double x = g0x, y = g0y;
     int it = 0;
-    while (norm2(x - GRIP0_X, y - GRIP0_Y) < 0.1f && it++ < MAX_SPAWN_ATTEMPTS) {
-        float u0, u1;
+    while (norm2(x - g0x, y - g0y) < 0.1 && it++ < MAX_SPAWN_ATTEMPTS) {
+        double u0, u1;
         rs_uniform2(env, 0, -r, r, &u0, &u1);
-        x = GRIP0_X + u0;
-        y = GRIP0_Y + u1;
+        x = g0x + u0;
+        y = g0y + u1;
     }
     for (int i = 0; i < nset; ++i) set_block_xy(env, i, x, y);
 }
 
 /* BlocksTouchEnv._randomize_objects fetch_env.py:370-399 */
 static void randomize_blocks_touch(bpo_env* env, int test) {
-    float r = (float)(test ? env->max_obj_range : env->obj_range);
-    float half = r / 2.0f;
-    float u0, u1;
-    rs_uniform2(env, 0, -half, half, &u0, &u1);
-    float x0 = GRIP0_X + u0, y0 = GRIP0_Y + u1;
+    const double g0x = (double)GRIP0_X, g0y = (double)GRIP0_Y;
+    double r = test ? env->max_obj_range : env->obj_range;
+    double u0, u1;
+    rs_uniform2(env, 0, -r / 2, r / 2, &u0, &u1);
+    double x0 = g0x + u0, y0 = g0y + u1;
     set_block_xy(env, 0, x0, y0);
-    float x, y;
+    double x, y;
     int it = 0;
     do {
         sample_around(env, x0, y0, MIN_BLOCK_DIST, r, &x, &y);
@@ -718,26 +744,26 @@ static void randomize_blocks_touch(bpo_env* env, int test) {
 }
 
 /* blue block: loop until on the table (fetch_env.py:475-480, 719-724) */
-static void sample_blue(bpo_env* env, float r, float* x, float* y) {
-    float half = r / 2.0f;
+static void sample_blue(bpo_env* env, double r, double* x, double* y) {
+    const double g0x = (double)GRIP0_X, g0y = (double)GRIP0_Y;
     int it = 0;
     do {
-        float u0, u1;
-        rs_uniform2(env, 0, -half, half, &u0, &u1);
-        *x = GRIP0_X + u0;
-        *y = GRIP0_Y + u1;
+        double u0, u1;
+        rs_uniform2(env, 0, -r / 2, r / 2, &u0, &u1);
+        *x = g0x + u0;
+        *y = g0y + u1;
     } while (out_of_table(*x, *y) && ++it < MAX_SPAWN_ATTEMPTS);
 }
 
 /* BlocksTouchChooseEnv._randomize_objects fetch_env.py:448-517 (challenge=False: tasks.py never sets it) */
 static void randomize_choose(bpo_env* env, int test) {
-    float r, wrong_r;
-    if (test) { r = (float)env->max_obj_range; wrong_r = 0.0f; }
-    else { r = (float)env->obj_range; wrong_r = (float)env->wrong_obj_range; }
-    float min_r = MIN_BLOCK_DIST;
-    float max_wrong_r = (float)env->max_obj_range;
+    double r, wrong_r;
+    if (test) { r = env->max_obj_range; wrong_r = 0.0; }
+    else { r = env->obj_range; wrong_r = env->wrong_obj_range; }
+    double min_r = MIN_BLOCK_DIST;
+    double max_wrong_r = env->max_obj_range;
     int blue = 1, green = 0, wrong = 2; /* colours [GREEN, BLUE, GREY], :465-473 */
-    float bx, by, gx, gy, wx, wy;
+    double bx, by, gx, gy, wx, wy;
     sample_blue(env, r, &bx, &by);
     set_block_xy(env, blue, bx, by);
     int it = 0;
@@ -745,7 +771,7 @@ static void randomize_choose(bpo_env* env, int test) {
         sample_around(env, bx, by, min_r, r, &gx, &gy);
     } while (out_of_table(gx, gy) && ++it < MAX_SPAWN_ATTEMPTS);
     set_block_xy(env, green, gx, gy);
-    float cx = (bx + gx) / 2.0f, cy = (by + gy) / 2.0f;
+    double cx = (bx + gx) / 2.0, cy = (by + gy) / 2.0;
     it = 0;
     int again;
     do {
@@ -759,11 +785,11 @@ static void randomize_choose(bpo_env* env, int test) {
 /* BlocksTouchVariationEnv._randomize_objects fetch_env.py:697-764 */
 static void randomize_variation(bpo_env* env, int test) {
     int num_blocks = env->num_objs - 2;
-    float r = (float)(test ? env->max_obj_range : env->obj_range);
+    double r = test ? env->max_obj_range : env->obj_range;
     int blue = 1, green = 0; /* colours [GREEN, BLUE, GREY, GREY], :710-716 */
-    float px[BPO_MAX_BLOCKS], py[BPO_MAX_BLOCKS];
+    double px[BPO_MAX_BLOCKS], py[BPO_MAX_BLOCKS];
     int np = 0;
-    float bx, by, gx, gy;
+    double bx, by, gx, gy;
     sample_blue(env, r, &bx, &by);
     set_block_xy(env, blue, bx, by);
     int it = 0;
@@ -775,13 +801,13 @@ static void randomize_variation(bpo_env* env, int test) {
     px[np] = gx; py[np] = gy; ++np;
     for (int i = 0; i < num_blocks; ++i) {
         if (i == blue || i == green) continue;
-        float x, y;
+        double x, y;
         int again;
         it = 0;
         do {
             /* _sample_from_table fetch_env.py:88-90: two scalar draws from self.np_random */
-            float ux = rs_uniform1(env, 0, -TABLE_W, TABLE_W);
-            float uy = rs_uniform1(env, 0, -TABLE_H, TABLE_H);
+            double ux = rs_uniform1(env, 0, -TABLE_W, TABLE_W);
+            double uy = rs_uniform1(env, 0, -TABLE_H, TABLE_H);
             x = TABLE_X + ux;
             y = TABLE_Y + uy;
             again = 0;
@@ -860,7 +886,7 @@ void bpo_env_get_obs(const bpo_env* env, float* obs, float* ag, float* g) {
         const bpo_block* b = &s->blk[i];
         obs[o++] = b->pos[0]; obs[o++] = b->pos[1]; obs[o++] = b->pos[2];
         obs[o++] = b->pos[0] - s->g[0]; obs[o++] = b->pos[1] - s->g[1]; obs[o++] = b->pos[2] - s->g[2];
-        obs[o++] = 0.0f; obs[o++] = 0.0f; obs[o++] = bpo_atan2(b->s, b->c); /* mat2euler of a pure yaw */
+        obs[o++] = -0.0f; obs[o++] = 0.0f; obs[o++] = bpo_atan2(b->s, b->c); /* mat2euler of a pure yaw: roll = -arctan2(0, 1) = -0.0 */
         obs[o++] = b->vel[0] * DT - gvp[0]; obs[o++] = b->vel[1] * DT - gvp[1]; obs[o++] = b->vel[2] * DT - gvp[2];
         obs[o++] = 0.0f; obs[o++] = 0.0f; obs[o++] = b->w * DT;
         if (var) { /* one_hot_color, :599 */
@@ -927,7 +953,7 @@ int bpo_env_increase_difficulty(bpo_env* env) {
             return 0;
         case BPO_BLOCKS_TOUCH_CHOOSE:
         case BPO_BLOCKS_TOUCH_CHOOSE_CURRICULUM:
-            if (!env->has_curriculum_step) return -1; /* AttributeError: no obj_range_step */
+            if (!env->has_curriculum_step) return -2; /* AttributeError: no obj_range_step (:413-415,420) */
             env->obj_range += env->obj_range_step;
             env->wrong_obj_range -= env->wrong_obj_range_step;
             if (env->obj_range > env->max_obj_range) {

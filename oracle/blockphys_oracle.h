@@ -6,17 +6,23 @@
  * (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline / --impl reference).
  * Nothing in blockpuzzle_gym_b200/ may include, link or call this file.
  *
- * PARITY STATUS: "parity unpinned" for the sim.step() slot.  The reference
- * delegates rigid-body dynamics to MuJoCo (robot_env.py:60), which is absent
- * from /root/reference and from this image, and the reference holds no tests,
- * golden vectors or fixtures.  The reference-OWNED
- * arithmetic (action map, touch matrix, obs layout, goal, reward, success
- * latch, spawn samplers, curriculum) is restated line by line and cited
- * function by function below; the dynamics slot is filled by the "BlockPhys v1"
- * model specified in DESIGN.md, which this file implements normatively.
+ * PARITY STATUS.  The reference-OWNED logic (action map, touch matrix, obs layout,
+ * goal, reward, success latch, spawn samplers, curriculum, TimeLimit) is restated
+ * line by line below AND PINNED to the reference's own code: oracle/refharness runs
+ * the unmodified /root/reference/gym_blocks under stub gym / mujoco_py packages with
+ * this file's BlockPhys model behind a fake MjSim and Philox behind the two numpy
+ * RNGs; tests/test_ref_pin.py compares that run with this restatement (integer state,
+ * draw counters and the binary32 sim state bit-exact; float64 observations within
+ * 1e-6) live when /root/reference or oracle/_ref is present and through the committed
+ * fixtures tests/golden/ref_*.npz otherwise.
+ * The sim.step() slot itself stays "own spec": the reference delegates rigid-body
+ * dynamics to MuJoCo (robot_env.py:60), absent from /root/reference and from this
+ * image; it is filled by the "BlockPhys v1.3" model of DESIGN.md, which this file
+ * implements normatively.
  *
- * All arithmetic is IEEE-754 binary32, round-to-nearest-even, every operation
- * individually rounded (compile with -ffp-contract=off, no -ffast-math).
+ * Dynamics arithmetic is IEEE-754 binary32, the spawn samplers binary64 (as the
+ * reference's numpy code), round-to-nearest-even, every operation individually
+ * rounded except the explicit fma()s (compile with -ffp-contract=off, no -ffast-math).
  */
 #ifndef BLOCKPHYS_ORACLE_H
 #define BLOCKPHYS_ORACLE_H
@@ -129,6 +135,8 @@ void bpo_normal2(uint32_t w0, uint32_t w1, float* z0, float* z1); /* Box-Muller 
 /* sim-level API (what mujoco_py offers the reference) */
 void bpo_sim_init(bpo_sim* sim, int env_id);       /* initial_state, robot_env.py:35 */
 void bpo_sim_set_action(bpo_sim* sim, const float a[4]); /* fetch_env.py:170-185 (after clip) */
+/* the same targets from what upstream utils.mocap_set_action / ctrl_set_action write (float64 mocap_pos, ctrl) */
+void bpo_sim_set_targets(bpo_sim* sim, const double mocap_pos[3], const double ctrl[2]);
 void bpo_sim_substep(bpo_sim* sim);
 void bpo_sim_step(bpo_sim* sim);                   /* 20 substeps, robot_env.py:60 */
 int bpo_pair_index(int o1, int o2);
@@ -141,7 +149,7 @@ void bpo_env_reset(bpo_env* env, float* obs, float* ag, float* g);  /* robot_env
 int bpo_env_step(bpo_env* env, const float action[4], float* obs, float* ag, float* g,
                  float* reward, int* is_success);
 int bpo_env_set_test(bpo_env* env, float* obs, float* ag, float* g);   /* 0 ok, -1 NotImplemented */
-int bpo_env_increase_difficulty(bpo_env* env);     /* 1 max reached, 0 not, -1 raises */
+int bpo_env_increase_difficulty(bpo_env* env);     /* 1 max reached, 0 not, -1 NotImplementedError, -2 AttributeError */
 int bpo_env_get_difficulty(const bpo_env* env);
 double bpo_env_get_obj_range(const bpo_env* env);
 void bpo_env_get_obs(const bpo_env* env, float* obs, float* ag, float* g);

@@ -105,6 +105,7 @@ def lib():
         L.bpo_vec_step_random.argtypes = [vp, C.c_int64, C.c_int, C.c_int, vp]
         L.bpo_sim_init.argtypes = [vp, C.c_int]
         L.bpo_sim_set_action.argtypes = [vp, vp]
+        L.bpo_sim_set_targets.argtypes = [vp, vp, vp]
         L.bpo_sim_step.argtypes = [vp]
         L.bpo_sim_substep.argtypes = [vp]
         assert L.bpo_sizeof_state() == STATE_DTYPE.itemsize, (L.bpo_sizeof_state(), STATE_DTYPE.itemsize)
@@ -178,6 +179,8 @@ class OracleVecEnv:
         rc = 0
         for i in range(self.n):
             rc = self.L.bpo_env_increase_difficulty(self._env_ptr(i))
+            if rc == -2:
+                raise AttributeError("'BlocksTouchChooseEnv' object has no attribute 'obj_range_step'")  # fetch_env.py:413-420
             if rc < 0:
                 raise NotImplementedError()
         return bool(rc)

@@ -5,7 +5,7 @@ reference tree and from this image; the reference has no tests or golden vectors
 
 Structure follows the reference one function at a time (paths relative to
 /root/reference/gym_blocks), with its own numpy-float32 arithmetic, and plugs the
-BlockPhys v1 C model (oracle/blockphys_oracle.c, via ctypes -- the role mujoco_py
+BlockPhys v1.3 C model (oracle/blockphys_oracle.c, via ctypes -- the role mujoco_py
 plays in the reference) into the `sim` slot:
 
     RobotEnv.seed / step / reset        envs/robot_env.py:53-82
@@ -39,18 +39,21 @@ GRIP0 = np.array([1.3419, 0.7491, 0.5347], f32)  # initial_gripper_xpos (pinned;
 MAX_SPAWN_ATTEMPTS = 10000
 
 
-def out_of_table(p):                            # fetch_env.py:30-32
-    return bool(abs(f32(p[0] - TABLE_X)) > TABLE_W or abs(f32(p[1] - TABLE_Y)) > TABLE_H)
+# the same constants as python floats, evaluated by the reference's own expressions (fetch_env.py:19-28)
+BLOCK_SIZE64 = 0.05
+MIN_BLOCK_DIST64 = 1.5 * BLOCK_SIZE64
+TABLE_X64, TABLE_Y64 = 1.05 + 0.25, 0.40 + 0.35
+TABLE_W64, TABLE_H64 = 0.25 - BLOCK_SIZE64 / 2, 0.35 - BLOCK_SIZE64 / 2
+
+
+def out_of_table64(pos):                        # fetch_env.py:30-32
+    return bool(abs(pos[0] - TABLE_X64) > TABLE_W64 or abs(pos[1] - TABLE_Y64) > TABLE_H64)
 
 
 def one_hot_color(c):                           # fetch_env.py:34-37
     r = np.zeros(NUM_COLORS, f32)
     r[c] = 1
     return r
-
-
-def norm2(v):                                   # np.linalg.norm of a 2-vector in fp32
-    return np.sqrt(f32(f32(v[0] * v[0]) + f32(v[1] * v[1])))
 
 
 # ---------------------------------------------------------------- Philox4x32-10 and the spec'd functions
@@ -161,19 +164,18 @@ class PhiloxRandomState:
         self.draws += 1
         return w
 
-    def uniform(self, low=0.0, high=1.0, size=None):
+    def uniform(self, low=0.0, high=1.0, size=None):        # numpy: low + (high - low) * u, float64
         w = self._block()
-        low, high = f32(low), f32(high)
-        span = f32(high - low)
+        low, high = float(low), float(high)
         if size is None:
-            return f32(low + f32(span * u01(w[0])))
+            return low + (high - low) * float(u01(w[0]))
         assert size == 2
-        return np.array([f32(low + f32(span * u01(w[0]))), f32(low + f32(span * u01(w[1])))], f32)
+        return np.array([low + (high - low) * float(u01(w[0])), low + (high - low) * float(u01(w[1]))], np.float64)
 
     def normal(self, size=2):
         assert size == 2
         w = self._block()
-        return bp_normal2(w[0], w[1])
+        return bp_normal2(w[0], w[1]).astype(np.float64)
 
     def randint(self, n):
         return (self._block()[0] * n) >> 32
@@ -409,7 +411,7 @@ class BlocksEnvOracle:
         for i in range(num_blocks):
             pos = sim.obj_pos(i)
             c, s = sim.obj_yaw_cs(i)
-            rot = np.array([0.0, 0.0, bp_atan2(s, c)], f32)     # mat2euler of a pure yaw
+            rot = np.array([-0.0, 0.0, bp_atan2(s, c)], f32)    # mat2euler of a pure yaw (roll = -arctan2(0, 1))
             velp = ((sim.obj_velp(i) * dt).astype(f32) - grip_velp).astype(f32)
             velr = (sim.obj_velr(i) * dt).astype(f32)
             parts += [pos, (pos - grip_pos).astype(f32), rot, velp, velr]
@@ -457,44 +459,44 @@ class BlocksEnvOracle:
                 "tower": [RED, GREEN, GREY, GREY, GREY, BLUE], "choose": [GREY, GREY, GREEN, BLUE, GREY],
                 "variation": [GREY, GREY, GREEN, BLUE, GREY, GREY]}[self.kind]
 
+    # The spawn samplers run in python floats / float64 arrays exactly like the reference (v1.3): only
+    # set_joint_qpos narrows object_xpos into the sim's binary32 state.
     def _sample_from_table(self):                               # fetch_env.py:88-90
-        return np.array([f32(TABLE_X + self.np_random.uniform(-TABLE_W, TABLE_W)),
-                         f32(TABLE_Y + self.np_random.uniform(-TABLE_H, TABLE_H))], f32)
+        return np.asarray([TABLE_X64 + self.np_random.uniform(-TABLE_W64, TABLE_W64),
+                           TABLE_Y64 + self.np_random.uniform(-TABLE_H64, TABLE_H64)])
 
     def _around(self, base, lo, hi):                            # fetch_env.py:390-393 and siblings
         direction = self.global_random.normal(size=2)
-        direction = (direction / norm2(direction)).astype(f32)
+        direction = direction / np.linalg.norm(direction)
         mag = self.global_random.uniform(lo, hi)
-        return (base + (direction * mag).astype(f32)).astype(f32)
+        return base + direction * mag
 
     def _randomize_objects(self, test=False):
-        g0 = self.initial_gripper_xpos[:2]
+        g0 = self.initial_gripper_xpos[:2].astype(np.float64)
         if self.kind in ("gripper", "tower"):                   # fetch_env.py:328-336, 777-787
             xy, it = g0, 0
-            r = f32(self.obj_range)
-            while norm2(xy - g0) < f32(0.1) and it < MAX_SPAWN_ATTEMPTS:
+            while np.linalg.norm(xy - g0) < 0.1 and it < MAX_SPAWN_ATTEMPTS:
                 it += 1
-                xy = (g0 + self.np_random.uniform(-r, r, size=2)).astype(f32)
+                xy = g0 + self.np_random.uniform(-self.obj_range, self.obj_range, size=2)
             for i in range(self.max_num_blocks):
                 self.sim.set_obj_xy(i, xy)
         elif self.kind == "touch":                              # fetch_env.py:370-399
-            r = f32(self.max_obj_range if test else self.obj_range)
-            half = f32(r / f32(2.0))
-            p0 = (g0 + self.np_random.uniform(-half, half, size=2)).astype(f32)
+            r = self.max_obj_range if test else self.obj_range
+            p0 = g0 + self.np_random.uniform(-r / 2, r / 2, size=2)
             self.sim.set_obj_xy(0, p0)
             it = 0
             while True:
-                xy = self._around(p0, MIN_BLOCK_DIST, r)
+                xy = self._around(p0, MIN_BLOCK_DIST64, r)
                 it += 1
-                if not out_of_table(xy) or it >= MAX_SPAWN_ATTEMPTS:
+                if not out_of_table64(xy) or it >= MAX_SPAWN_ATTEMPTS:
                     break
             self.sim.set_obj_xy(1, xy)
         elif self.kind == "choose":                             # fetch_env.py:448-517
             if test:
-                r, wrong_r = f32(self.max_obj_range), f32(0)
+                r, wrong_r = self.max_obj_range, 0
             else:
-                r, wrong_r = f32(self.obj_range), f32(self.wrong_obj_range)
-            max_wrong_r = f32(self.max_obj_range)
+                r, wrong_r = self.obj_range, self.wrong_obj_range
+            max_wrong_r = self.max_obj_range
             blocks = self.obj_colors[2:5]
             blue, green = blocks.index(BLUE), blocks.index(GREEN)
             wrong = [i for i in range(3) if i not in (blue, green)][0]
@@ -502,18 +504,19 @@ class BlocksEnvOracle:
             self.sim.set_obj_xy(blue, pb)
             pg = self._green(pb, r)
             self.sim.set_obj_xy(green, pg)
-            centre = ((pb + pg).astype(f32) / f32(2.0)).astype(f32)
+            centre = (pb + pg) / 2.0
             it = 0
             while True:
                 xy = self._around(centre, wrong_r, max_wrong_r)
                 it += 1
-                bad = out_of_table(xy) or norm2(xy - pb) < MIN_BLOCK_DIST or norm2(xy - pg) < MIN_BLOCK_DIST
+                bad = (out_of_table64(xy) or np.linalg.norm(xy - pb) < MIN_BLOCK_DIST64
+                       or np.linalg.norm(xy - pg) < MIN_BLOCK_DIST64)
                 if not bad or it >= MAX_SPAWN_ATTEMPTS:
                     break
             self.sim.set_obj_xy(wrong, xy)
         else:                                                   # variation, fetch_env.py:697-764
             num_blocks = self.num_objs - 2
-            r = f32(self.max_obj_range if test else self.obj_range)
+            r = self.max_obj_range if test else self.obj_range
             blocks = self.obj_colors[2:2 + num_blocks]
             blue, green = blocks.index(BLUE), blocks.index(GREEN)
             pb = self._blue(r)
@@ -529,32 +532,31 @@ class BlocksEnvOracle:
                     xy = self._sample_from_table()
                     it += 1
                     for p in placed:
-                        if norm2(xy - p) < MIN_BLOCK_DIST:
+                        if np.linalg.norm(xy - p) < MIN_BLOCK_DIST64:
                             again = True
                             break
                     else:
-                        again = out_of_table(xy)
+                        again = out_of_table64(xy)
                     if not again or it >= MAX_SPAWN_ATTEMPTS:
                         break
                 self.sim.set_obj_xy(i, xy)
                 placed.append(xy)
 
     def _blue(self, r):                                         # fetch_env.py:475-480, 719-724
-        g0 = self.initial_gripper_xpos[:2]
-        half = f32(r / f32(2.0))
+        g0 = self.initial_gripper_xpos[:2].astype(np.float64)
         it = 0
         while True:
-            xy = (g0 + self.np_random.uniform(-half, half, size=2)).astype(f32)
+            xy = g0 + self.np_random.uniform(-r / 2, r / 2, size=2)
             it += 1
-            if not out_of_table(xy) or it >= MAX_SPAWN_ATTEMPTS:
+            if not out_of_table64(xy) or it >= MAX_SPAWN_ATTEMPTS:
                 return xy
 
     def _green(self, pb, r):                                    # fetch_env.py:488-494, 732-738
         it = 0
         while True:
-            xy = self._around(pb, MIN_BLOCK_DIST, r)
+            xy = self._around(pb, MIN_BLOCK_DIST64, r)
             it += 1
-            if not out_of_table(xy) or it >= MAX_SPAWN_ATTEMPTS:
+            if not out_of_table64(xy) or it >= MAX_SPAWN_ATTEMPTS:
                 return xy
 
     # ---- curriculum ----

@@ -1,0 +1,1 @@
+from .registration import make, register, registry, spec  # noqa: F401

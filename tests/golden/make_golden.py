@@ -1,9 +1,9 @@
-"""Generates the golden fixtures of tests/golden/ from the C oracle (oracle/blockphys_oracle.c).
+"""Generates the auto-reset / HER fixtures of tests/golden/ from the C oracle (oracle/blockphys_oracle.c).
 
-The reference (matthew9671/BlockPuzzle-gym) ships no tests, golden vectors or fixtures, and it
-cannot be imported here (gym, mujoco_py, baselines are absent), so these vectors pin the
-BlockPhys v1 spec + the restated env logic at the commit that froze them; they are NOT outputs
-of the reference.  Run from the repo root:  python tests/golden/make_golden.py
+These vectors (<id>.npz, her_relabel.npz) pin the batched conveniences the reference does not have --
+auto-reset inside a fused launch, the Philox HER sampler -- at the commit that froze them; they are
+oracle outputs.  The fixtures recorded from the REFERENCE ITSELF are ref_<id>.npz (make_ref_golden.py),
+and the oracle is pinned to those.  Run from the repo root:  python tests/golden/make_golden.py
 """
 import os
 import sys

@@ -1,0 +1,48 @@
+"""Shared pieces of the "reference callers, unmodified" tests (CPU: on the reference's own envs; GPU: on the drop-in)."""
+import types
+
+import numpy as np
+
+
+class QuantisedPolicy(object):
+    """A seeded closed-loop stand-in for DDPG.get_actions (ddpg.py:122-156) / PGGD.get_actions: reads o, ag and g,
+    returns actions on a 1/8 grid in [-1.25, 1.25] (some outside the action box: the env clips).  Quantising makes
+    the action insensitive to the <= 1e-6 float64-vs-binary32 differences of the observations it reads, so the
+    same policy drives bit-identical episodes on the reference env and on the CUDA drop-in."""
+
+    def __init__(self, dimo, dimg, env_name, seed=3):
+        rng = np.random.RandomState(seed)
+        self.Wo = rng.normal(size=(dimo, 4)) * 2.0
+        self.Wg = rng.normal(size=(dimg, 4)) * 0.3
+        self.kwargs = {"info": {"env_name": env_name}}     # what policy_gradient/rollout.py:49,119,148 read
+        self.calls = 0
+
+    def _u(self, o, ag, g):
+        x = np.asarray(o, np.float64) @ self.Wo + (np.asarray(ag, np.float64) - np.asarray(g, np.float64)) @ self.Wg
+        self.calls += 1
+        return (np.round(np.tanh(x) * 10.0) / 8.0).astype(np.float32)
+
+    # gym_blocks/rollout.py:92-97
+    def get_actions(self, o, ag, g, compute_Q=False, noise_eps=0., random_eps=0., use_target_net=False, exploit=None):
+        u = self._u(o, ag, g)
+        if exploit is not None:                              # policy_gradient/rollout.py:199-201: (u, raw, sigma)
+            return u, u.copy(), np.zeros_like(u)
+        return u
+
+
+def dims_of(env):
+    """config.configure_dims (config.py:159-183) without the cached env: o / u / g / info_is_success."""
+    obs = env.reset()
+    return {"o": obs["observation"].shape[0], "u": 4, "g": obs["desired_goal"].shape[0], "info_is_success": 1}
+
+
+class QuietLogger(object):
+    def info(self, *a):
+        pass
+
+    warning = warn = info
+
+
+def fake_pg_self(env_name):
+    """`self` for calling policy_gradient RolloutStudent.trim (rollout.py:105-171) straight from its source."""
+    return types.SimpleNamespace(kwargs={"info": {"env_name": env_name}})

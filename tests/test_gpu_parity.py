@@ -161,7 +161,7 @@ def test_not_implemented_paths():
         with pytest.raises(NotImplementedError):
             env.increase_difficulty()
     env = bpg.make_vec("BlocksTouchChoose-v0", 8, device=0)
-    with pytest.raises(NotImplementedError):  # AttributeError in the reference: no obj_range_step
+    with pytest.raises(AttributeError):       # the reference never sets obj_range_step (fetch_env.py:413-415,420)
         env.increase_difficulty()
 
 
