@@ -44,8 +44,10 @@ SYMBOLS = {
     "bp_seed": (_i, [_vp, _u64, _vp]),
     "bp_reset": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "bp_step": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    "bp_step_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i]),
+    "bp_step_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "bp_rollout": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "bp_rollout_begin": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "bp_rollout_step": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "bp_set_test": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "bp_increase_difficulty": (_i, [_vp, C.POINTER(_i)]),
     "bp_get_difficulty": (_i, [_vp, C.POINTER(_i)]),
@@ -85,7 +87,7 @@ def load():
             fn = getattr(L, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.bp_abi_version() != 1:
+        if L.bp_abi_version() != 2:
             raise BlockPuzzleError("ABI version mismatch")
         _lib = L
     return _lib

@@ -31,7 +31,7 @@ struct Async {
     static constexpr int NB = C::NB;
     static constexpr int CS = 32 * E;                       // envs per warp = column stride of the slab
     static constexpr int W_CUB = 9 * NB * CS, W_GRP = 10 * CS, W_MSC = 3 * CS;
-    static constexpr int W_COL = Col<NB, CS, 32>::kScratch * 32;  // per-lane substep scratch of a full-physics pass (the cubes are stepped in place)
+    static constexpr int W_COL = 0;                          // (round 1 kept 4*NB*32 words of per-lane substep scratch here: the pass now runs in registers)
     static constexpr int W_PEND = CS / 2;                    // uint16 pending list
     static constexpr int W_BITS = kMaxFused * E;             // reward bits of every (step, env) of the launch
     static constexpr size_t SMEM = sizeof(uint32_t) * (size_t)(W_CUB + W_GRP + W_MSC + W_COL + W_PEND + W_BITS);
@@ -114,7 +114,7 @@ __device__ __noinline__ uint32_t finalize_step(uint32_t contacts, float* cub, fl
     const bool fail = env_post_step<ID>(contacts, touch_now, touch_ever, succ, t);
     const bool done = t >= kT;
     msc[0] = touch_now | (touch_ever << 16);
-    msc[CS] = pf_make(pf, (uint32_t)t | ((uint32_t)succ << 8) | ((uint32_t)nb << 9));
+    msc[CS] = pf_make(pf, (uint32_t)(t < 255 ? t : 255) | ((uint32_t)succ << 8) | ((uint32_t)nb << 9));   // t saturates in its 8 bits (auto_reset = 0 callers may step past T)
     if (fail) atomicOr(bits_word, bit);          // reward bit of (k, env): flushed as whole rows at the end (the latched
                                                  // success rows are rebuilt from these bits there, see slab_flush)
     if (done_out) *done_out = done ? 1 : 0;
@@ -148,7 +148,7 @@ __device__ __forceinline__ uint32_t finalize_at(const StepArgs& p, int64_t li, i
     const int64_t row = step_row(p, k, li), orow = obs_row(p, k, li);
     return finalize_step<ID, CS>(contacts, s_cub + w, s_grp + w, s_msc + w, s_bits + (k * E + (w >> 5)), 1u << (w & 31),
                                  p.done ? p.done + row : nullptr,
-                                 (p.actions && k + 1 < p.K) ? reinterpret_cast<const float4*>(p.actions) + ((int64_t)(p.k0 + k + 1) * p.B + li) : nullptr,
+                                 (p.actions && k + 1 < p.K) ? reinterpret_cast<const float4*>(p.actions) + ((int64_t)(p.act_k0 + k + 1) * p.B + li) : nullptr,
                                  p.goal_out ? p.goal_out + row * C::DIMG : nullptr,
                                  p.obs ? p.obs + orow * C::DIMO : nullptr,
                                  p.ag ? p.ag + orow * C::DIMG : nullptr);
@@ -160,7 +160,7 @@ __device__ __forceinline__ float4 fetch_action(const uint32_t* __restrict__ st, 
     constexpr int NF = num_fields<Cfg<ID>::NB>();
     float4 a4;
     if (p.actions) {  // the action tensor is always time-major [Ktot][B][4]
-        a4 = __ldg(reinterpret_cast<const float4*>(p.actions) + ((int64_t)(p.k0 + k) * p.B + li));
+        a4 = __ldg(reinterpret_cast<const float4*>(p.actions) + ((int64_t)(p.act_k0 + k) * p.B + li));
     } else {
         const int64_t gi = p.env0 + li;
         const uint32_t ep = st[(int64_t)(NF - 5) * p.stateB + gi];
@@ -228,12 +228,11 @@ __device__ __forceinline__ uint32_t try_quiet_step(uint32_t* __restrict__ st, co
     return 1u | (code << 1);
 }
 
-// One full-physics env-step of slab column pw at step k, stepped in place in the slab (s_scr: this lane's
-// substep scratch).  A private per-lane copy of the cubes avoided bank conflicts between pass items but
-// cost 2.3 KB of the slab; the slab's size decides how many warps an SM holds.
+// One full-physics env-step of slab column pw at step k: the env's cubes are loaded into registers, stepped there
+// (sim_step_reg) and written back to the slab column.
 template <int ID, int E>
 __device__ __forceinline__ uint32_t full_step_item(uint32_t* __restrict__ st, const StepArgs& p, int64_t li, int pw, int k,
-                                               float* s_scr, float* s_cub, float* s_grp, uint32_t* s_msc,
+                                               float* s_cub, float* s_grp, uint32_t* s_msc,
                                                uint32_t* s_bits, WarpStats& ws) {
     using C = Cfg<ID>;
     constexpr int NB = C::NB, CS = 32 * E;
@@ -247,7 +246,20 @@ __device__ __forceinline__ uint32_t full_step_item(uint32_t* __restrict__ st, co
     for (int d = 0; d < 3; ++d) { g.g[d] = s_grp[d * CS + pw]; g.gv[d] = s_grp[(3 + d) * CS + pw]; }
     g.q[0] = s_grp[6 * CS + pw]; g.q[1] = s_grp[7 * CS + pw]; g.qv[0] = s_grp[8 * CS + pw]; g.qv[1] = s_grp[9 * CS + pw];
     uint32_t contacts = 0;
-    const bool is_static = sim_step_col<NB, CS, C::BG>(g, a, Col<NB, CS, 32>(s_cub + pw, s_scr), (int)((flags >> 9) & 7u), contacts);
+    CubeRegs<NB> q;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const float* bb = s_cub + (9 * b) * CS + pw;
+        q.x[b] = bb[0]; q.y[b] = bb[CS]; q.z[b] = bb[2 * CS]; q.c[b] = bb[3 * CS]; q.s[b] = bb[4 * CS];
+        q.vx[b] = bb[5 * CS]; q.vy[b] = bb[6 * CS]; q.vz[b] = bb[7 * CS]; q.w[b] = bb[8 * CS];
+    }
+    const bool is_static = sim_step_reg<NB, C::BG, C::VAR>(g, a, q, (int)((flags >> 9) & 7u), contacts);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        float* bb = s_cub + (9 * b) * CS + pw;
+        bb[0] = q.x[b]; bb[CS] = q.y[b]; bb[2 * CS] = q.z[b]; bb[3 * CS] = q.c[b]; bb[4 * CS] = q.s[b];
+        bb[5 * CS] = q.vx[b]; bb[6 * CS] = q.vy[b]; bb[7 * CS] = q.vz[b]; bb[8 * CS] = q.w[b];
+    }
 #pragma unroll
     for (int d = 0; d < 3; ++d) { s_grp[d * CS + pw] = g.g[d]; s_grp[(3 + d) * CS + pw] = g.gv[d]; }
     s_grp[6 * CS + pw] = g.q[0]; s_grp[7 * CS + pw] = g.q[1]; s_grp[8 * CS + pw] = g.qv[0]; s_grp[9 * CS + pw] = g.qv[1];
@@ -373,13 +385,12 @@ __global__ void __launch_bounds__(32, E == 4 ? 12 : (E == 3 ? 15 : 20)) step_ker
     float* s_cub = reinterpret_cast<float*>(smem);                    // [9*NB][CS]
     float* s_grp = s_cub + A::W_CUB;                                  // [10][CS]
     uint32_t* s_msc = reinterpret_cast<uint32_t*>(s_grp + A::W_GRP);  // [4][CS]: touch, flags, priv, status
-    float* s_col = reinterpret_cast<float*>(s_msc + A::W_MSC);        // [4*NB][32] per-lane substep scratch
+    float* s_col = reinterpret_cast<float*>(s_msc + A::W_MSC);
     uint16_t* s_pend = reinterpret_cast<uint16_t*>(s_col + A::W_COL); // [CS]
     uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_col + A::W_COL) + A::W_PEND;  // [K][E]: reward-fail masks over 32 envs
 
     const int lane = threadIdx.x;
     const int64_t wbase = (int64_t)blockIdx.x * CS;  // launch-local index of the warp's env 0
-    float* const wscr = s_col + lane;
     WarpStats ws;
 
     // ---- load the slab: env (e, lane) is launch-local env wbase + e*32 + lane, slab column e*32 + lane
@@ -436,7 +447,7 @@ __global__ void __launch_bounds__(32, E == 4 ? 12 : (E == 3 ? 15 : 20)) step_ker
             if (lane < take) {
                 pw = s_pend[lane];
                 const int k = (int)(s_msc[2 * CS + pw] & 0xffffu);
-                const uint32_t code = full_step_item<ID, E>(st, p, wbase + pw, pw, k, wscr, s_cub, s_grp, s_msc, s_bits, ws);
+                const uint32_t code = full_step_item<ID, E>(st, p, wbase + pw, pw, k, s_cub, s_grp, s_msc, s_bits, ws);
                 rs = p.auto_reset && (code & 2u);
                 s_msc[2 * CS + pw] = (uint32_t)(k + 1) | (rs ? kPendingBit : 0u);  // clears the pending flag unless a reset is due
             }
@@ -488,6 +499,7 @@ __global__ void __launch_bounds__(32, E == 4 ? 12 : (E == 3 ? 15 : 20)) step_ker
     }
 }
 
+#ifdef BP_EXPERIMENTS
 // ---------------------------------------------------------------------------------------------------
 // step_kernel_duo (BP_STEP_KERNEL=duo; an EXPERIMENT kept for the record, not the default): the same
 // slab and the same env-step functions, served by TWO warps.
@@ -625,7 +637,6 @@ __global__ void __launch_bounds__(64, 10) step_kernel_duo(uint32_t* __restrict__
         named_bar_arrive(kBarFull, 64);
     } else {
         // ================================================= worker
-        float* const wscr = s_col + lane;
         uint32_t epoch = 0;
         while (true) {
             named_bar_sync(kBarFull, 64);
@@ -635,7 +646,7 @@ __global__ void __launch_bounds__(64, 10) step_kernel_duo(uint32_t* __restrict__
             if (lane < take) {
                 pw = s_batch[lane];
                 k = (int)(s_msc[2 * CS + pw] & 0xffffu);
-                const uint32_t code = full_step_item<ID, E>(st, p, wbase + pw, pw, k, wscr, s_cub, s_grp, s_msc, s_bits, ws);
+                const uint32_t code = full_step_item<ID, E>(st, p, wbase + pw, pw, k, s_cub, s_grp, s_msc, s_bits, ws);
                 if (p.auto_reset && (code & 2u)) reset_env_slab<ID, CS>(st, p, wbase + pw, s_cub + pw, s_grp + pw, s_msc + pw);
             }
             __threadfence_block();                        // the env's state before its status word
@@ -656,5 +667,7 @@ __global__ void __launch_bounds__(64, 10) step_kernel_duo(uint32_t* __restrict__
         atomicAdd(p.stats + 7, (double)n_pass);
     }
 }
+
+#endif  // BP_EXPERIMENTS
 
 }  // namespace bp

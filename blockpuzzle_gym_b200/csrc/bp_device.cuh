@@ -323,7 +323,9 @@ __device__ __forceinline__ bool over_table(float x, float y) {
 }
 
 // finger f (0: +y, 1: -y) against cube b (index bi); ox/oy: the cube's start-of-substep position
-__device__ __forceinline__ void collide_finger_block(Grip& e, GripSub& st, const int f, Blk& b, const float ox, const float oy,
+// Returns false when the pair is not penetrating (nothing but `contacts` was touched), true when the response ran
+// and the cube, the gripper height or the finger opening may have changed.
+__device__ __forceinline__ bool collide_finger_block(Grip& e, GripSub& st, const int f, Blk& b, const float ox, const float oy,
                                                      float& dth_acc, bool& rotated, uint32_t& sup, uint32_t& contacts, const int bi) {
     const float sgn = f == 0 ? 1.0f : -1.0f;
     const float qf = f == 0 ? e.q[0] : e.q[1];
@@ -333,13 +335,13 @@ __device__ __forceinline__ void collide_finger_block(Grip& e, GripSub& st, const
     float dz = b.z - az;
     float ovz = (kFZ + kHB) - fabsf(dz);
     Sat o;
-    if (!sat_eval<true>(A, B, o, ovz)) return;
+    if (!sat_eval<true>(A, B, o, ovz)) return false;
     float minxy;
     int k = sat_argmin(o, minxy);
     float minov = ovz < minxy ? ovz : minxy;
-    if (!(minov > -kMargin)) return;
+    if (!(minov > -kMargin)) return false;
     contacts |= pair_bit(0, 2) << bi;  // pair (0, bi+2): any "finger" geom -> object 0 (fetch_env.py:111-112)
-    if (!(minov > 0.0f)) return;
+    if (!(minov > 0.0f)) return false;
     if (ovz <= minxy) {
         if (dz >= 0.0f) {
             b.z = az + (kFZ + kHB);
@@ -348,7 +350,7 @@ __device__ __forceinline__ void collide_finger_block(Grip& e, GripSub& st, const
             e.g[2] = (b.z + (kFZ + kHB)) - kFZOff;
             if (e.gv[2] < 0.0f) e.gv[2] = 0.0f;
         }
-        return;
+        return true;
     }
     float delta = minxy;
     float q_now = qf;
@@ -365,7 +367,7 @@ __device__ __forceinline__ void collide_finger_block(Grip& e, GripSub& st, const
                 else { e.q[1] = q_now; e.qv[1] = 0.0f; st.closed[1] = closed - yield; }
                 delta = delta - yield;
             }
-            if (!(delta > 0.0f)) return;
+            if (!(delta > 0.0f)) return true;
         }
     }
     float nx, ny, rnA, rnB;
@@ -376,7 +378,7 @@ __device__ __forceinline__ void collide_finger_block(Grip& e, GripSub& st, const
     float rel = F((b.x - ox) - fdx, nx, ((b.y - oy) - fdy) * ny);
     float cap = kDepen - rel;
     float lam = delta < cap ? delta : cap;
-    if (!(lam > 0.0f)) return;
+    if (!(lam > 0.0f)) return true;
     float D = F(kIInv, rnB * rnB, 1.0f);
     float l = lam / D;
     b.x = F(nx, l, b.x);
@@ -387,10 +389,11 @@ __device__ __forceinline__ void collide_finger_block(Grip& e, GripSub& st, const
         dth_acc = dth_acc + dth;
         rotated = true;
     }
+    return true;
 }
 
 // cubes i < j; aox.. are their start-of-substep positions
-__device__ __forceinline__ void collide_block_block(Blk& a, const float aox, const float aoy, float& adth,
+__device__ __forceinline__ bool collide_block_block(Blk& a, const float aox, const float aoy, float& adth,
                                                     Blk& b, const float box, const float boy, float& bdth,
                                                     bool& rotated, uint32_t& sup, uint32_t& contacts, const int i, const int j) {
     Rect A{a.x, a.y, a.c, a.s, kHB, kHB};
@@ -398,27 +401,27 @@ __device__ __forceinline__ void collide_block_block(Blk& a, const float aox, con
     float dz = b.z - a.z;
     float ovz = kTwoHB - fabsf(dz);
     Sat o;
-    if (!sat_eval<false>(A, B, o, ovz)) return;
+    if (!sat_eval<false>(A, B, o, ovz)) return false;
     float minxy;
     int k = sat_argmin(o, minxy);
     float minov = ovz < minxy ? ovz : minxy;
-    if (!(minov > -kMargin)) return;
+    if (!(minov > -kMargin)) return false;
     contacts |= 1u << pair_index(i + 2, j + 2);  // "objectK" -> K + 2 (fetch_env.py:115-116)
-    if (!(minov > 0.0f)) return;
+    if (!(minov > 0.0f)) return false;
     int pin = 0;
     if (ovz <= minxy) {
         if (dz >= 0.0f) {
             if (fabsf(o.proj[0]) <= kHB && fabsf(o.proj[1]) <= kHB) {
                 b.z = a.z + kTwoHB;
                 sup |= 1u << j;
-                return;
+                return true;
             }
             pin = 1;
         } else {
             if (fabsf(o.proj[2]) <= kHB && fabsf(o.proj[3]) <= kHB) {
                 a.z = b.z + kTwoHB;
                 sup |= 1u << i;
-                return;
+                return true;
             }
             pin = 2;
         }
@@ -428,7 +431,7 @@ __device__ __forceinline__ void collide_block_block(Blk& a, const float aox, con
     float rel = F((b.x - box) - (a.x - aox), nx, ((b.y - boy) - (a.y - aoy)) * ny);
     float cap = kDepen - rel;
     float lam = minxy < cap ? minxy : cap;
-    if (!(lam > 0.0f)) return;
+    if (!(lam > 0.0f)) return true;
     float wA = pin == 1 ? 0.0f : 1.0f;
     float wB = pin == 2 ? 0.0f : 1.0f;
     float D = F(kIInv, F(wA, rnA * rnA, wB * (rnB * rnB)), wA + wB);
@@ -442,6 +445,7 @@ __device__ __forceinline__ void collide_block_block(Blk& a, const float aox, con
     float dthB = (kIInv * rnB) * lB;
     if (dthA != 0.0f) { rot_apply(a.c, a.s, dthA); adth = adth + dthA; rotated = true; }
     if (dthB != 0.0f) { rot_apply(b.c, b.s, dthB); bdth = bdth + dthB; rotated = true; }
+    return true;
 }
 
 // the gripper part of one substep (steps 1-2 of the spec)
@@ -625,6 +629,208 @@ __device__ __forceinline__ bool sim_step_col(Grip& g, const float a[4], const Co
         GripSub st;
         substep_gripper<BG>(g, st, m, ctrl);
         still = substep_cubes<NB, STRIDE, SS>(g, st, col, nb, contacts);
+    }
+    return still;
+}
+
+// ---------------------------------------------------------------- the same step with the cubes in registers
+// sim_step_col above walks the cubes through shared-memory loops and evaluates every (finger, cube) and (cube, cube)
+// slot of every substep in turn: the contact-response tails then run once per slot with the one or two lanes of the
+// warp that need them (ncu, round 1: 19 % of the kernel's issue slots at <= 4 active lanes).  Here the cubes of one
+// env live in registers for the whole env-step, the per-cube stages are unrolled, and the contact stage is
+//   (1) branch-free candidate masks: stage 1 of the separating-axis test (z and the first rectangle's two axes -- the
+//       same expressions sat_eval evaluates first) for every slot at once;
+//   (2) while (mask): pop the lowest slot, run the UNCHANGED collide_* function on it.
+// A slot outside the mask would have returned from sat_eval's first test without touching anything, so skipping it
+// is exact; slots are still visited in the oracle's Gauss-Seidel order (fingers cube-major, then pairs i-major), and
+// whenever a response may have moved something the masks of the later slots are recomputed from the current state.
+// Arithmetic per slot is identical: results stay bit-for-bit those of sim_step_col and of the oracle.
+template <int NB>
+struct CubeRegs {
+    float x[NB], y[NB], z[NB], c[NB], s[NB], vx[NB], vy[NB], vz[NB], w[NB];   // state
+    float ox[NB], oy[NB], oz[NB], dth[NB];                                    // start-of-substep position, yaw change
+};
+
+template <int NB>
+__device__ __forceinline__ float pick(const float (&a)[NB], const int i) {
+    float r = a[0];
+#pragma unroll
+    for (int k = 1; k < NB; ++k) r = (i == k) ? a[k] : r;
+    return r;
+}
+template <int NB>
+__device__ __forceinline__ void put(float (&a)[NB], const int i, const float v) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) a[k] = (i == k) ? v : a[k];
+}
+
+// bit 2i + f: finger f passes stage 1 of sat_eval<true> against cube i (see collide_finger_block)
+template <int NB, bool VAR>
+__device__ __forceinline__ uint32_t finger_candidates(const Grip& e, const CubeRegs<NB>& q, const int nb) {
+    const float az = e.g[2] + kFZOff;
+    const float ay0 = e.g[1] + (kFY0 + e.q[0]);
+    const float ay1 = e.g[1] - (kFY0 + e.q[1]);
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        const float C = fabsf(q.c[i]), S = fabsf(q.s[i]);
+        const float RBu = F(kHB, C, kHB * S);
+        const float RBv = F(kHB, S, kHB * C);
+        const float ov0 = (kFX + RBu) - fabsf(q.x[i] - e.g[0]);
+        const float ovz = (kFZ + kHB) - fabsf(q.z[i] - az);
+        const bool common = (!VAR || i < nb) && ovz > -kMargin && ov0 > -kMargin;
+        const float ov1a = (kFY + RBv) - fabsf(q.y[i] - ay0);
+        const float ov1b = (kFY + RBv) - fabsf(q.y[i] - ay1);
+        m |= (common && ov1a > -kMargin) ? (1u << (2 * i)) : 0u;
+        m |= (common && ov1b > -kMargin) ? (2u << (2 * i)) : 0u;
+    }
+    return m;
+}
+
+// bit p: pair p = (i, j), i-major, passes stage 1 of sat_eval<false> (see collide_block_block)
+template <int NB, bool VAR>
+__device__ __forceinline__ uint32_t pair_candidates(const CubeRegs<NB>& q, const int nb) {
+    uint32_t m = 0;
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i + 1 < NB; ++i) {
+#pragma unroll
+        for (int j = i + 1; j < NB; ++j) {
+            const float cr = F(q.c[i], q.c[j], q.s[i] * q.s[j]);
+            const float sr = F(q.c[i], q.s[j], -(q.s[i] * q.c[j]));
+            const float C = fabsf(cr), S = fabsf(sr);
+            const float dx = q.x[j] - q.x[i], dy = q.y[j] - q.y[i];
+            const float RBu = F(kHB, C, kHB * S);
+            const float RBv = F(kHB, S, kHB * C);
+            const float p0 = F(dx, q.c[i], dy * q.s[i]);
+            const float p1 = F(dy, q.c[i], -(dx * q.s[i]));
+            const float ov0 = (kHB + RBu) - fabsf(p0);
+            const float ov1 = (kHB + RBv) - fabsf(p1);
+            const float ovz = kTwoHB - fabsf(q.z[j] - q.z[i]);
+            const bool ok = (!VAR || j < nb) && ovz > -kMargin && ov0 > -kMargin && ov1 > -kMargin;
+            m |= ok ? (1u << p) : 0u;
+            ++p;
+        }
+    }
+    return m;
+}
+
+template <int NB, bool VAR>
+__device__ __forceinline__ bool substep_cubes_reg(Grip& e, GripSub& st, CubeRegs<NB>& q, const int nb, uint32_t& contacts) {
+    uint32_t sup = 0;
+    bool rest = true, rotated = false;
+    contacts = 0;
+    // 3. predict + 4a. table / floor support
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (!VAR || i < nb) {
+            rest = rest && q.vx[i] == 0.0f && q.vy[i] == 0.0f && q.vz[i] == 0.0f && q.w[i] == 0.0f;
+            q.ox[i] = q.x[i]; q.oy[i] = q.y[i]; q.oz[i] = q.z[i];
+            float dth = 0.0f;
+            q.vz[i] = q.vz[i] - kGH;
+            q.x[i] = F(q.vx[i], kH, q.x[i]);
+            q.y[i] = F(q.vy[i], kH, q.y[i]);
+            q.z[i] = F(q.vz[i], kH, q.z[i]);
+            if (q.w[i] != 0.0f) {
+                dth = q.w[i] * kH;
+                rot_apply(q.c[i], q.s[i], dth);
+                rotated = true;
+            }
+            q.dth[i] = dth;
+            const bool ot = over_table(q.x[i], q.y[i]);
+            const bool touch_t = ot && (q.z[i] - kZRest < kMargin);
+            const bool on_t = ot && q.z[i] < kZRest;
+            const bool on_f = !ot && q.z[i] < kZFloor;
+            contacts |= touch_t ? (pair_bit(1, 2) << i) : 0u;
+            q.z[i] = on_t ? kZRest : (on_f ? kZFloor : q.z[i]);
+            sup |= (on_t || on_f) ? (1u << i) : 0u;
+        }
+    }
+    // 4b. fingers vs cubes
+    uint32_t fm = finger_candidates<NB, VAR>(e, q, nb);
+    while (fm) {
+        const int slot = __ffs((int)fm) - 1;
+        fm &= fm - 1u;
+        const int i = slot >> 1, f = slot & 1;
+        Blk b{pick<NB>(q.x, i), pick<NB>(q.y, i), pick<NB>(q.z, i), pick<NB>(q.c, i), pick<NB>(q.s, i), 0.0f, 0.0f, 0.0f, 0.0f};
+        float dth = pick<NB>(q.dth, i);
+        if (collide_finger_block(e, st, f, b, pick<NB>(q.ox, i), pick<NB>(q.oy, i), dth, rotated, sup, contacts, i)) {
+            put<NB>(q.x, i, b.x); put<NB>(q.y, i, b.y); put<NB>(q.z, i, b.z); put<NB>(q.c, i, b.c); put<NB>(q.s, i, b.s);
+            put<NB>(q.dth, i, dth);
+            fm = finger_candidates<NB, VAR>(e, q, nb) & ~((2u << slot) - 1u);
+        }
+    }
+    // 4c. cube pairs
+    if (NB > 1) {
+        uint32_t pm = pair_candidates<NB, VAR>(q, nb);
+        while (pm) {
+            const int slot = __ffs((int)pm) - 1;
+            pm &= pm - 1u;
+            int i = 0, j = 1, p = 0;
+#pragma unroll
+            for (int a = 0; a + 1 < NB; ++a) {
+#pragma unroll
+                for (int b = a + 1; b < NB; ++b) {
+                    if (slot == p) { i = a; j = b; }
+                    ++p;
+                }
+            }
+            Blk a{pick<NB>(q.x, i), pick<NB>(q.y, i), pick<NB>(q.z, i), pick<NB>(q.c, i), pick<NB>(q.s, i), 0.0f, 0.0f, 0.0f, 0.0f};
+            Blk b{pick<NB>(q.x, j), pick<NB>(q.y, j), pick<NB>(q.z, j), pick<NB>(q.c, j), pick<NB>(q.s, j), 0.0f, 0.0f, 0.0f, 0.0f};
+            float adth = pick<NB>(q.dth, i), bdth = pick<NB>(q.dth, j);
+            if (collide_block_block(a, pick<NB>(q.ox, i), pick<NB>(q.oy, i), adth, b, pick<NB>(q.ox, j), pick<NB>(q.oy, j), bdth,
+                                    rotated, sup, contacts, i, j)) {
+                put<NB>(q.x, i, a.x); put<NB>(q.y, i, a.y); put<NB>(q.z, i, a.z); put<NB>(q.c, i, a.c); put<NB>(q.s, i, a.s);
+                put<NB>(q.dth, i, adth);
+                put<NB>(q.x, j, b.x); put<NB>(q.y, j, b.y); put<NB>(q.z, j, b.z); put<NB>(q.c, j, b.c); put<NB>(q.s, j, b.s);
+                put<NB>(q.dth, j, bdth);
+                pm = pair_candidates<NB, VAR>(q, nb) & ~((2u << slot) - 1u);
+            }
+        }
+    }
+    // 4d. fingers vs table
+    if (over_table(e.g[0], e.g[1]) && e.g[2] - kGZMin < kMargin) contacts |= pair_bit(0, 1);
+    // 5. velocities from the position change, then Coulomb friction on supported cubes
+    bool same = rest && !rotated;
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        if (!VAR || i < nb) {
+            same = same && __float_as_uint(q.x[i]) == __float_as_uint(q.ox[i]) && __float_as_uint(q.y[i]) == __float_as_uint(q.oy[i]) &&
+                   __float_as_uint(q.z[i]) == __float_as_uint(q.oz[i]);
+            float vx = clampf((q.x[i] - q.ox[i]) * kInvH, -kVMax, kVMax);
+            float vy = clampf((q.y[i] - q.oy[i]) * kInvH, -kVMax, kVMax);
+            const float vz = clampf((q.z[i] - q.oz[i]) * kInvH, -kVMax, kVMax);
+            float w = clampf(q.dth[i] * kInvH, -kWMax, kWMax);
+            const bool supd = (sup >> i & 1u) != 0u;
+            const float sp2 = F(vx, vx, vy * vy);
+            if (supd && sp2 > kFr * kFr) {
+                const float sp = sqrtf(sp2);
+                const float kf = (sp - kFr) / sp;
+                vx = vx * kf;
+                vy = vy * kf;
+            } else if (supd) {
+                vx = 0.0f; vy = 0.0f;
+            }
+            const float wdec = w > 0.0f ? w - kFrW : w + kFrW;
+            w = supd ? ((fabsf(w) <= kFrW) ? 0.0f : wdec) : w;
+            same = same && vx == 0.0f && vy == 0.0f && vz == 0.0f && w == 0.0f;
+            q.vx[i] = vx; q.vy[i] = vy; q.vz[i] = vz; q.w[i] = w;
+        }
+    }
+    return same;
+}
+
+// _set_action + sim.step() on a register-resident env (full-physics pass of the async step kernel)
+template <int NB, bool BG, bool VAR>
+__device__ __forceinline__ bool sim_step_reg(Grip& g, const float a[4], CubeRegs<NB>& q, const int nb, uint32_t& contacts) {
+    float m[3], ctrl[2];
+    action_targets<BG>(g, a, m, ctrl);
+    bool still = false;
+#pragma unroll 1
+    for (int sub = 0; sub < kNSub; ++sub) {
+        GripSub st;
+        substep_gripper<BG>(g, st, m, ctrl);
+        still = substep_cubes_reg<NB, VAR>(g, st, q, nb, contacts);
     }
     return still;
 }

@@ -61,7 +61,7 @@ __device__ __forceinline__ void store_env(uint32_t* __restrict__ st, int64_t B, 
         stf(e.vx[b]); stf(e.vy[b]); stf(e.vz[b]); stf(e.w[b]);
     }
     stu(e.touch_now | (e.touch_ever << 16));
-    stu((uint32_t)e.t | ((uint32_t)e.succ << 8) | ((uint32_t)e.nb << 9));
+    stu((uint32_t)(e.t < 255 ? e.t : 255) | ((uint32_t)e.succ << 8) | ((uint32_t)e.nb << 9));   // t saturates: any t >= T behaves alike (TimeLimit keeps done = True)
     stu(e.priv);
     stu(e.episode); stu(e.draws0); stu(e.draws1);
     stu(e.key0); stu(e.key1);
@@ -162,6 +162,7 @@ struct StepArgs {
     // obs / ag are [B][Ktot + 1] with the reset observation in slot 0 -> row li * (Ktot + 1) + k0 + k + 1.
     int layout;
     int k0;
+    int act_k0;            // row of `actions` that holds step k0's actions (== k0, or 0 for the per-step tensor of bp_rollout_step)
     int Ktot;
     float* goal_out;       // layout 1: desired_goal rows [B][Ktot][DIMG] (nullable)
     int tune;              // duo kernel: minimum ready lanes for a scheduler iteration while the worker is busy
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(128) step_kernel_simple(uint32_t* st, StepArgs
     }
 }
 
+#ifdef BP_EXPERIMENTS   // lab notebook: the CTA-tiled kernel of the first design (make EXPERIMENTS=1)
 // ---------------------------------------------------------------- tiled step kernel
 // One CTA of 128 threads owns a tile of 256 envs for all K fused steps.  Cube state lives in shared
 // memory (SoA), the gripper state of each env in the registers of its owner thread (2 envs/thread).
@@ -608,6 +610,8 @@ __global__ void __launch_bounds__(128, 4) step_kernel_tiled(uint32_t* __restrict
     }
 }
 
+#endif  // BP_EXPERIMENTS
+
 }  // namespace bp
 
 #include "bp_async.cuh"
@@ -735,6 +739,7 @@ __global__ void compute_reward_kernel(const float* __restrict__ ag, const float*
     store_reward(r + i, d != (float)c);
 }
 
+#ifdef BP_EXPERIMENTS   // the original thread-per-transition relabel kernel (43 % of HBM), superseded by her_sample_kernel
 // HER relabel + reward (baselines.her.her._sample_her_transitions [upstream]; config.py:107-123)
 __global__ void her_relabel_kernel(const float* __restrict__ ep_ag, const float* __restrict__ ep_g, int B, int T, int dimg,
                                    int64_t n, float future_p, uint32_t k0, uint32_t k1, int64_t index_offset,
@@ -776,6 +781,8 @@ __global__ void her_relabel_kernel(const float* __restrict__ ep_ag, const float*
     if (fut_t) fut_t[i] = her ? ft : -1;
 }
 
+#endif  // BP_EXPERIMENTS
+
 }  // namespace bp
 
 // ======================================================================= C-ABI
@@ -790,6 +797,21 @@ static int fail(int code, const std::string& msg) { return bp_fail(code, msg); }
         if (_e != cudaSuccess)                                                                \
             return fail(BP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));      \
     } while (0)
+
+// Entry points run on the handle's device and leave the caller's current device as they found it (torch reads it
+// through cudaGetDevice: a library that switches it silently redirects the caller's later allocations).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) err = cudaSetDevice(dev); else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(h)                                                                          \
+    DeviceGuard _dg((h)->device);                                                             \
+    if (_dg.err != cudaSuccess) return fail(BP_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_dg.err))
 
 static const char* kNames[BP_NUM_ENV_IDS] = {
     "GripperTouch-v0", "BlocksTouch-v0", "ToppleTower-v0", "BlocksTouchCurriculum-v0",
@@ -815,6 +837,7 @@ struct bp_handle {
     cudaStream_t hs[2] = {nullptr, nullptr};
     float* d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
+    cudaEvent_t ev = nullptr;       // orders the staging streams after the caller's stream
 };
 
 static Ranges ranges_of(const bp_handle* h) {
@@ -837,17 +860,27 @@ static int dispatch(int env_id, F&& f) {
 
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
-// BP_STEP_KERNEL = async (default) | duo | tiled | simple
+// BP_STEP_KERNEL = async (default) | simple (full physics for every env-step: the cross-check of the quiet path and
+// the scheduler); built with -DBP_EXPERIMENTS also duo | tiled
 static int step_kernel_choice() {
     static const int v = [] {
         const char* e = getenv("BP_STEP_KERNEL");
         if (e && strcmp(e, "simple") == 0) return 2;
+#ifdef BP_EXPERIMENTS
         if (e && strcmp(e, "tiled") == 0) return 1;
         if (e && strcmp(e, "duo") == 0) return 3;
+#endif
         return 0;
     }();
     return v;
 }
+
+// cudaFuncSetAttribute is per device: remember which devices a kernel has been configured on
+struct AttrOnce {
+    unsigned long long done = 0;   // bit d: set on device d (devices >= 64 are configured on every launch)
+    bool need(int dev) const { return dev < 0 || dev >= 64 || !((done >> dev) & 1ull); }
+    void mark(int dev) { if (dev >= 0 && dev < 64) done |= 1ull << dev; }
+};
 
 template <class K>
 static int set_smem_attr(K kernel, size_t bytes) {
@@ -861,19 +894,21 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
     int rc = dispatch(h->env_id, [&](auto id) {
         constexpr int ID = decltype(id)::value;
         const int choice = step_kernel_choice();
-        if (a.layout != 0 && choice != 0 && choice != 3) return fail(BP_ERR_INVALID_ARG, "the batch-major episode layout needs the async / duo step kernel");
+        if (a.layout != 0 && choice != 0 && choice != 3) return fail(BP_ERR_INVALID_ARG, "the batch-major episode layout needs the async step kernel");
         if (choice == 2) {
             constexpr size_t kSmem = sizeof(float) * Col<Cfg<ID>::NB, 128>::kFields * 128;
             step_kernel_simple<ID><<<nblk(a.B, 128), 128, kSmem, s>>>(h->d_state, a);
+#ifdef BP_EXPERIMENTS
         } else if (choice == 1) {
             using T = Tile<ID>;
-            static bool attr_set[BP_NUM_ENV_IDS] = {};
-            if (!attr_set[ID]) {
+            static AttrOnce once;
+            if (once.need(h->device)) {
                 int r = set_smem_attr(step_kernel_tiled<ID>, T::SMEM + pad);
                 if (r != BP_OK) return r;
-                attr_set[ID] = true;
+                once.mark(h->device);
             }
             step_kernel_tiled<ID><<<nblk(a.B, T::TILE), T::THREADS, T::SMEM + pad, s>>>(h->d_state, a);
+#endif
         } else {
             // envs per lane (tuning).  Measured at the 18 KB slab, resident warps in brackets: E = 2 [20] 2.22e9, 3 [15] 3.16e9,
             // 4 [12] 3.28e9, 5 [10] 3.23e9, 6 [8] 3.08e9 env-steps/s
@@ -883,12 +918,14 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
             auto go = [&](auto ec) -> int {
                 constexpr int E = decltype(ec)::value;
                 using A = Async<ID, E>;
-                static bool attr_set = false;
-                if (!attr_set) {
+                static AttrOnce once;
+                if (once.need(h->device)) {
                     int r = set_smem_attr(step_kernel_async<ID, E>, A::SMEM + pad);
+#ifdef BP_EXPERIMENTS
                     if (r == BP_OK) r = set_smem_attr(step_kernel_duo<ID, E>, Duo<ID, E>::SMEM + pad);
+#endif
                     if (r != BP_OK) return r;
-                    attr_set = true;
+                    once.mark(h->device);
                 }
                 // the kernel keeps the reward / success bits of at most kMaxFused steps on chip: split longer K
                 // async: reset-pass threshold | full-physics-pass threshold << 8; duo: minimum ready lanes (tuning knobs)
@@ -904,8 +941,11 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                     c.tune = tune;
                     c.K = (a.K - k0) < kMaxFused ? (a.K - k0) : kMaxFused;
                     c.k0 = a.k0 + k0;
-                    if (choice == 3) step_kernel_duo<ID, E><<<nblk(a.B, A::CS), 64, Duo<ID, E>::SMEM + pad, s>>>(h->d_state, c);
-                    else step_kernel_async<ID, E><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
+                    c.act_k0 = a.act_k0 + k0;
+#ifdef BP_EXPERIMENTS
+                    if (choice == 3) { step_kernel_duo<ID, E><<<nblk(a.B, A::CS), 64, Duo<ID, E>::SMEM + pad, s>>>(h->d_state, c); continue; }
+#endif
+                    step_kernel_async<ID, E><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
                 }
                 return (int)BP_OK;
             };
@@ -952,7 +992,8 @@ int bp_create(int env_id, int64_t num_envs, int device, uint64_t env_index_offse
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(BP_ERR_NO_DEVICE, "no CUDA device: blockpuzzle_b200 has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(BP_ERR_INVALID_ARG, "bad device index");
-    CU(cudaSetDevice(device));
+    DeviceGuard dg(device);
+    if (dg.err != cudaSuccess) return fail(BP_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(dg.err));
     bp_handle* h = new bp_handle();
     h->env_id = env_id; h->device = device; h->B = num_envs; h->env_offset = env_index_offset;
     h->nf = 18 + 9 * kNB[env_id];
@@ -973,7 +1014,8 @@ int bp_create(int env_id, int64_t num_envs, int device, uint64_t env_index_offse
         cudaFree(h->d_state); cudaFree(h->d_stats); delete h;
         return fail(BP_ERR_CUDA, "cudaMalloc of env state failed");
     }
-    cudaMemset(h->d_stats, 0, sizeof(double) * BP_NUM_STATS);
+    cudaError_t e0 = cudaMemset(h->d_stats, 0, sizeof(double) * BP_NUM_STATS);
+    if (e0 != cudaSuccess) { bp_destroy(h); return fail(BP_ERR_CUDA, std::string("cudaMemset of the statistics vector: ") + cudaGetErrorString(e0)); }
     int rc = dispatch(env_id, [&](auto id) {
         init_kernel<decltype(id)::value><<<nblk(num_envs, 128), 128>>>(h->d_state, num_envs);
         return BP_OK;
@@ -988,13 +1030,14 @@ int bp_create(int env_id, int64_t num_envs, int device, uint64_t env_index_offse
 
 int bp_destroy(bp_handle* h) {
     if (!h) return BP_OK;
-    cudaSetDevice(h->device);
+    DeviceGuard dg(h->device);
     cudaFree(h->d_state);
     cudaFree(h->d_stats);
     for (int i = 0; i < 2; ++i) {
         if (h->d_stage[i]) cudaFree(h->d_stage[i]);
         if (h->hs[i]) cudaStreamDestroy(h->hs[i]);
     }
+    if (h->ev) cudaEventDestroy(h->ev);
     delete h;
     return BP_OK;
 }
@@ -1003,7 +1046,7 @@ int64_t bp_num_envs(const bp_handle* h) { return h ? h->B : 0; }
 
 int bp_seed(bp_handle* h, uint64_t seed, void* stream) {
     if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     seed_kernel<<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, h->nf, seed, h->env_offset);
     CU(cudaGetLastError());
     return BP_OK;
@@ -1011,7 +1054,7 @@ int bp_seed(bp_handle* h, uint64_t seed, void* stream) {
 
 int bp_reset(bp_handle* h, const uint8_t* d_mask, float* d_obs, float* d_ag, float* d_g, void* stream) {
     if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     Ranges rg = ranges_of(h);
     int rc = dispatch(h->env_id, [&](auto id) {
         reset_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, d_mask, rg, d_obs, d_ag, d_g, 1);
@@ -1027,13 +1070,38 @@ int bp_step(bp_handle* h, const float* d_actions, int K, float* d_obs, float* d_
             float* d_actions_out, void* stream) {
     if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
     if (K <= 0 || K > 65535) return fail(BP_ERR_INVALID_ARG, "K must be in 1..65535");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     StepArgs a{};
     a.actions = d_actions; a.obs = d_obs; a.ag = d_ag; a.reward = d_reward; a.success = d_success; a.done = d_done;
     a.reset_obs = d_reset_obs; a.reset_ag = d_reset_ag; a.actions_out = d_actions_out; a.stats = h->d_stats;
     a.B = h->B; a.stateB = h->B; a.env0 = 0; a.K = K; a.auto_reset = auto_reset; a.rg = ranges_of(h);
-    a.layout = 0; a.k0 = 0; a.Ktot = K; a.goal_out = nullptr;
+    a.layout = 0; a.k0 = 0; a.act_k0 = 0; a.Ktot = K; a.goal_out = nullptr;
     return launch_step(h, a, (cudaStream_t)stream);
+}
+
+// reset_all_rollouts (rollout.py:48-64): reset(), then set_test() for test rollouts; slot 0 of the episode's o / ag
+static int rollout_reset(bp_handle* h, int test, float* d_o, float* d_ag, float* d_g0, cudaStream_t s) {
+    const int T = BP_MAX_EPISODE_STEPS;
+    if (test && (h->env_id == BP_GRIPPER_TOUCH || h->env_id == BP_TOPPLE_TOWER))
+        return fail(BP_ERR_NOT_IMPLEMENTED, "set_test raises NotImplementedError for this env (fetch_env.py:100-101)");
+    Ranges rg = ranges_of(h);
+    int rc = dispatch(h->env_id, [&](auto id) {
+        constexpr int ID = decltype(id)::value;
+        reset_kernel<ID><<<nblk(h->B, 128), 128, 0, s>>>(h->d_state, h->B, nullptr, rg, d_o, d_ag, d_g0, T + 1);
+        return (int)BP_OK;
+    });
+    if (rc != BP_OK) return rc;
+    CU(cudaGetLastError());
+    if (test) {
+        rc = dispatch(h->env_id, [&](auto id) {
+            constexpr int ID = decltype(id)::value;
+            set_test_kernel<ID><<<nblk(h->B, 128), 128, 0, s>>>(h->d_state, h->B, rg, d_o, d_ag, d_g0, T + 1);
+            return (int)BP_OK;
+        });
+        if (rc != BP_OK) return rc;
+        CU(cudaGetLastError());
+    }
+    return BP_OK;
 }
 
 int bp_rollout(bp_handle* h, const float* d_actions, int test, float* d_o, float* d_ag, float* d_g, float* d_u,
@@ -1041,42 +1109,48 @@ int bp_rollout(bp_handle* h, const float* d_actions, int test, float* d_o, float
     if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
     if (!d_o || !d_ag) return fail(BP_ERR_INVALID_ARG, "bp_rollout needs the o and ag episode tensors");
     if (step_kernel_choice() != 0) return fail(BP_ERR_INVALID_ARG, "bp_rollout needs the async step kernel");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const int T = BP_MAX_EPISODE_STEPS;
-    Ranges rg = ranges_of(h);
     cudaStream_t s = (cudaStream_t)stream;
-    // reset_all_rollouts (rollout.py:48-64): reset(), then set_test() for test rollouts; slot 0 of o / ag
-    int rc = dispatch(h->env_id, [&](auto id) {
-        constexpr int ID = decltype(id)::value;
-        reset_kernel<ID><<<nblk(h->B, 128), 128, 0, s>>>(h->d_state, h->B, nullptr, rg, d_o, d_ag, nullptr, T + 1);
-        return (int)BP_OK;
-    });
+    int rc = rollout_reset(h, test, d_o, d_ag, nullptr, s);
     if (rc != BP_OK) return rc;
-    CU(cudaGetLastError());
-    if (test) {
-        if (h->env_id == BP_GRIPPER_TOUCH || h->env_id == BP_TOPPLE_TOWER)
-            return fail(BP_ERR_NOT_IMPLEMENTED, "set_test raises NotImplementedError for this env (fetch_env.py:100-101)");
-        rc = dispatch(h->env_id, [&](auto id) {
-            constexpr int ID = decltype(id)::value;
-            set_test_kernel<ID><<<nblk(h->B, 128), 128, 0, s>>>(h->d_state, h->B, rg, d_o, d_ag, nullptr, T + 1);
-            return (int)BP_OK;
-        });
-        if (rc != BP_OK) return rc;
-        CU(cudaGetLastError());
-    }
     StepArgs a{};
     a.actions = d_actions; a.obs = d_o; a.ag = d_ag; a.reward = d_reward; a.success = d_success; a.actions_out = d_u;
     a.goal_out = d_g; a.stats = h->d_stats;
-    a.B = h->B; a.stateB = h->B; a.env0 = 0; a.K = T; a.auto_reset = 0; a.rg = rg;
-    a.layout = 1; a.k0 = 0; a.Ktot = T;
+    a.B = h->B; a.stateB = h->B; a.env0 = 0; a.K = T; a.auto_reset = 0; a.rg = ranges_of(h);
+    a.layout = 1; a.k0 = 0; a.act_k0 = 0; a.Ktot = T;
     return launch_step(h, a, s);
 }
 
+int bp_rollout_begin(bp_handle* h, int test, float* d_o, float* d_ag, float* d_g0, void* stream) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    if (!d_o || !d_ag) return fail(BP_ERR_INVALID_ARG, "bp_rollout_begin needs the o and ag episode tensors");
+    ON_DEVICE(h);
+    return rollout_reset(h, test, d_o, d_ag, d_g0, (cudaStream_t)stream);
+}
+
+int bp_rollout_step(bp_handle* h, int t, const float* d_actions, float* d_o, float* d_ag, float* d_g, float* d_u,
+                    float* d_success, float* d_reward, void* stream) {
+    if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
+    if (t < 0 || t >= BP_MAX_EPISODE_STEPS) return fail(BP_ERR_INVALID_ARG, "t must be in 0..T-1");
+    if (!d_actions || !d_o || !d_ag) return fail(BP_ERR_INVALID_ARG, "bp_rollout_step needs actions [B][4] and the o / ag episode tensors");
+    if (step_kernel_choice() != 0) return fail(BP_ERR_INVALID_ARG, "bp_rollout_step needs the async step kernel");
+    ON_DEVICE(h);
+    StepArgs a{};
+    a.actions = d_actions; a.obs = d_o; a.ag = d_ag; a.reward = d_reward; a.success = d_success; a.actions_out = d_u;
+    a.goal_out = d_g; a.stats = h->d_stats;
+    a.B = h->B; a.stateB = h->B; a.env0 = 0; a.K = 1; a.auto_reset = 0; a.rg = ranges_of(h);
+    a.layout = 1; a.k0 = t; a.act_k0 = 0; a.Ktot = BP_MAX_EPISODE_STEPS;
+    return launch_step(h, a, (cudaStream_t)stream);
+}
+
+static inline size_t align4(size_t nfloats) { return (nfloats + 3) & ~(size_t)3; }   // sub-buffers start on 16 bytes (float4 row stores)
+
 int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, float* h_ag, float* h_reward,
-                 float* h_success, int auto_reset) {
+                 float* h_success, int auto_reset, void* stream) {
     if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
     if (K <= 0 || K > 65535 || !h_actions) return fail(BP_ERR_INVALID_ARG, "bp_step_host needs actions and K in 1..65535");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const int dimo = kDimO[h->env_id], dimg = kDimG[h->env_id];
     // chunk of envs: per env and step 4 (action) + dimo + dimg + 2 floats
     const size_t per_env = (size_t)K * (size_t)(4 + dimo + dimg + 2) * sizeof(float);
@@ -1084,16 +1158,32 @@ int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, floa
     if (chunk > h->B) chunk = h->B;
     chunk &= ~(int64_t)127;
     if (chunk < 128) chunk = h->B < 128 ? h->B : 128;
-    const size_t need = per_env * (size_t)chunk;
+    const size_t need = per_env * (size_t)chunk + 5 * 16;   // + the alignment padding of the five sub-buffers
     if (h->stage_bytes < need) {
         for (int i = 0; i < 2; ++i) {
             if (h->d_stage[i]) cudaFree(h->d_stage[i]);
             h->d_stage[i] = nullptr;
+            h->stage_bytes = 0;
             CU(cudaMalloc(&h->d_stage[i], need));
             if (!h->hs[i]) CU(cudaStreamCreateWithFlags(&h->hs[i], cudaStreamNonBlocking));
         }
         h->stage_bytes = need;
     }
+    if (!h->ev) CU(cudaEventCreateWithFlags(&h->ev, cudaEventDisableTiming));
+    // the staging streams start after whatever the caller has queued on its own stream (bp_seed / bp_reset /
+    // bp_set_state / bp_step run there): without this the first step kernel could overtake a pending reset
+    CU(cudaEventRecord(h->ev, (cudaStream_t)stream));
+    CU(cudaStreamWaitEvent(h->hs[0], h->ev, 0));
+    CU(cudaStreamWaitEvent(h->hs[1], h->ev, 0));
+    // on any error both staging streams are drained before returning: no copy into the caller's arrays is left in flight
+#define CUH(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            cudaStreamSynchronize(h->hs[0]); cudaStreamSynchronize(h->hs[1]);                 \
+            return fail(BP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));      \
+        }                                                                                     \
+    } while (0)
     // the host arrays are [K][B][dim]; a chunk [K][n][dim] is strided -> 2-D copies
     int buf = 0;
     for (int64_t e0 = 0; e0 < h->B; e0 += chunk, buf ^= 1) {
@@ -1101,25 +1191,28 @@ int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, floa
         cudaStream_t s = h->hs[buf];
         float* base = h->d_stage[buf];
         float* d_act = base;
-        float* d_obs = d_act + (size_t)K * n * 4;
-        float* d_ag = d_obs + (size_t)K * n * dimo;
-        float* d_r = d_ag + (size_t)K * n * dimg;
-        float* d_s = d_r + (size_t)K * n;
-        CU(cudaMemcpy2DAsync(d_act, (size_t)n * 4 * 4, h_actions + e0 * 4, (size_t)h->B * 4 * 4, (size_t)n * 4 * 4, K, cudaMemcpyHostToDevice, s));
+        float* d_obs = d_act + align4((size_t)K * n * 4);
+        float* d_ag = d_obs + align4((size_t)K * n * dimo);
+        float* d_r = d_ag + align4((size_t)K * n * dimg);
+        float* d_s = d_r + align4((size_t)K * n);
+        CUH(cudaMemcpy2DAsync(d_act, (size_t)n * 4 * 4, h_actions + e0 * 4, (size_t)h->B * 4 * 4, (size_t)n * 4 * 4, K, cudaMemcpyHostToDevice, s));
         StepArgs a{};
         a.actions = d_act; a.obs = h_obs ? d_obs : nullptr; a.ag = h_ag ? d_ag : nullptr;
         a.reward = h_reward ? d_r : nullptr; a.success = h_success ? d_s : nullptr;
         a.stats = h->d_stats; a.B = n; a.stateB = h->B; a.env0 = e0; a.K = K; a.auto_reset = auto_reset; a.rg = ranges_of(h);
-        a.layout = 0; a.k0 = 0; a.Ktot = K; a.goal_out = nullptr;
+        a.layout = 0; a.k0 = 0; a.act_k0 = 0; a.Ktot = K; a.goal_out = nullptr;
         int rc = launch_step(h, a, s);
-        if (rc != BP_OK) return rc;
-        if (h_obs) CU(cudaMemcpy2DAsync(h_obs + e0 * dimo, (size_t)h->B * dimo * 4, d_obs, (size_t)n * dimo * 4, (size_t)n * dimo * 4, K, cudaMemcpyDeviceToHost, s));
-        if (h_ag) CU(cudaMemcpy2DAsync(h_ag + e0 * dimg, (size_t)h->B * dimg * 4, d_ag, (size_t)n * dimg * 4, (size_t)n * dimg * 4, K, cudaMemcpyDeviceToHost, s));
-        if (h_reward) CU(cudaMemcpy2DAsync(h_reward + e0, (size_t)h->B * 4, d_r, (size_t)n * 4, (size_t)n * 4, K, cudaMemcpyDeviceToHost, s));
-        if (h_success) CU(cudaMemcpy2DAsync(h_success + e0, (size_t)h->B * 4, d_s, (size_t)n * 4, (size_t)n * 4, K, cudaMemcpyDeviceToHost, s));
+        if (rc != BP_OK) { cudaStreamSynchronize(h->hs[0]); cudaStreamSynchronize(h->hs[1]); return rc; }
+        if (h_obs) CUH(cudaMemcpy2DAsync(h_obs + e0 * dimo, (size_t)h->B * dimo * 4, d_obs, (size_t)n * dimo * 4, (size_t)n * dimo * 4, K, cudaMemcpyDeviceToHost, s));
+        if (h_ag) CUH(cudaMemcpy2DAsync(h_ag + e0 * dimg, (size_t)h->B * dimg * 4, d_ag, (size_t)n * dimg * 4, (size_t)n * dimg * 4, K, cudaMemcpyDeviceToHost, s));
+        if (h_reward) CUH(cudaMemcpy2DAsync(h_reward + e0, (size_t)h->B * 4, d_r, (size_t)n * 4, (size_t)n * 4, K, cudaMemcpyDeviceToHost, s));
+        if (h_success) CUH(cudaMemcpy2DAsync(h_success + e0, (size_t)h->B * 4, d_s, (size_t)n * 4, (size_t)n * 4, K, cudaMemcpyDeviceToHost, s));
     }
-    CU(cudaStreamSynchronize(h->hs[0]));
-    CU(cudaStreamSynchronize(h->hs[1]));
+#undef CUH
+    cudaError_t s0 = cudaStreamSynchronize(h->hs[0]);
+    cudaError_t s1 = cudaStreamSynchronize(h->hs[1]);
+    if (s0 != cudaSuccess || s1 != cudaSuccess)
+        return fail(BP_ERR_CUDA, std::string("bp_step_host: ") + cudaGetErrorString(s0 != cudaSuccess ? s0 : s1));
     return BP_OK;
 }
 
@@ -1127,7 +1220,7 @@ int bp_set_test(bp_handle* h, float* d_obs, float* d_ag, float* d_g, void* strea
     if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
     if (h->env_id == BP_GRIPPER_TOUCH || h->env_id == BP_TOPPLE_TOWER)
         return fail(BP_ERR_NOT_IMPLEMENTED, "set_test raises NotImplementedError for this env (fetch_env.py:100-101)");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     Ranges rg = ranges_of(h);
     int rc = dispatch(h->env_id, [&](auto id) {
         set_test_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, rg, d_obs, d_ag, d_g, 1);
@@ -1192,7 +1285,7 @@ int bp_set_ranges(bp_handle* h, double obj_range, double wrong_obj_range) {
 
 int bp_get_state(bp_handle* h, bp_env_state* d_out, void* stream) {
     if (!h || !d_out) return fail(BP_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     int rc = dispatch(h->env_id, [&](auto id) {
         get_state_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, d_out);
         return BP_OK;
@@ -1204,7 +1297,7 @@ int bp_get_state(bp_handle* h, bp_env_state* d_out, void* stream) {
 
 int bp_set_state(bp_handle* h, const bp_env_state* d_in, void* stream) {
     if (!h || !d_in) return fail(BP_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     int rc = dispatch(h->env_id, [&](auto id) {
         set_state_kernel<decltype(id)::value><<<nblk(h->B, 128), 128, 0, (cudaStream_t)stream>>>(h->d_state, h->B, d_in);
         return BP_OK;
@@ -1222,7 +1315,7 @@ int bp_stats_ptr(bp_handle* h, double** d_stats) {
 
 int bp_stats_reset(bp_handle* h, void* stream) {
     if (!h) return fail(BP_ERR_INVALID_ARG, "null handle");
-    CU(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CU(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * BP_NUM_STATS, (cudaStream_t)stream));
     return BP_OK;
 }
@@ -1256,16 +1349,18 @@ int bp_her_relabel(const float* d_ep_ag, const float* d_ep_g, int32_t B, int32_t
     if (B <= 0 || T <= 0 || dimg <= 0 || n < 0) return fail(BP_ERR_INVALID_ARG, "bad sizes");
     if (n == 0) return BP_OK;
     if (!d_ep_ag || !d_ep_g) return fail(BP_ERR_INVALID_ARG, "null episode store");
-    // the goal / reward subset of the transition sampler: same draw, same kernel (block-cooperative row gathers;
-    // the original thread-per-transition her_relabel_kernel reached 43 % of HBM, BP_HER_RELABEL_LEGACY=1 selects it)
+    // the goal / reward subset of the transition sampler: same draw, same kernel (block-cooperative row gathers)
+#ifdef BP_EXPERIMENTS
     static const bool legacy = [] { const char* e = getenv("BP_HER_RELABEL_LEGACY"); return e && atoi(e) != 0; }();
-    if (legacy || dimg > 256) {
+    if (legacy) {
         her_relabel_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(d_ep_ag, d_ep_g, B, T, dimg, n, future_p,
                                                                           (uint32_t)seed, (uint32_t)(seed >> 32), index_offset,
                                                                           d_ep_idx, d_t, d_future_t, d_ag2, d_g, d_r);
         CU(cudaGetLastError());
         return BP_OK;
     }
+#endif
+    if (dimg > 256) return fail(BP_ERR_INVALID_ARG, "dimg > 256 is not supported (the registered ids have dimg <= 36)");
     return bp_her_sample(nullptr, nullptr, d_ep_g, d_ep_ag, nullptr, B, T, 1, 0, dimg, n, future_p, 0.0f, seed, index_offset,
                          d_ep_idx, d_t, d_future_t, nullptr, nullptr, nullptr, d_g, nullptr, d_ag2, d_r, nullptr, nullptr, stream);
 }

@@ -172,7 +172,10 @@ class VecBlocksEnv:
         out = {} if out is None else out
 
         def buf(name, *shape, dtype=torch.float32):
-            if name not in out or out[name] is None:
+            t = out.get(name)
+            # a reused buffer is handed to the kernel as a raw pointer: it must be exactly what the kernel will write
+            if (t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype or t.device != self.device
+                    or not t.is_contiguous()):
                 out[name] = self._empty(*shape, dtype=dtype)
             return out[name]
 
@@ -197,14 +200,17 @@ class VecBlocksEnv:
             out = dict(observation=np.empty((K, B, self.dimo), np.float32), achieved_goal=np.empty((K, B, self.dimg), np.float32),
                        reward=np.empty((K, B), np.float32), is_success=np.empty((K, B), np.float32))
         p = lambda x: C.c_void_p(x.ctypes.data)
+        for k, shp in (("observation", (K, B, self.dimo)), ("achieved_goal", (K, B, self.dimg)), ("reward", (K, B)), ("is_success", (K, B))):
+            x = out[k]
+            assert x.shape == shp and x.dtype == np.float32 and x.flags.c_contiguous, (k, x.shape, x.dtype)
         check(self.L.bp_step_host(self._h, p(a), K, p(out["observation"]), p(out["achieved_goal"]), p(out["reward"]),
-                                  p(out["is_success"]), int(bool(auto_reset))))
+                                  p(out["is_success"]), int(bool(auto_reset)), _stream(self.device)))
         return out
 
     def step_host_ptrs(self, a_ptr, K, obs_ptr, ag_ptr, r_ptr, s_ptr, auto_reset=True):
         """bp_step_host on raw host addresses (e.g. pinned torch tensors' data_ptr())."""
         check(self.L.bp_step_host(self._h, C.c_void_p(a_ptr), K, C.c_void_p(obs_ptr), C.c_void_p(ag_ptr),
-                                  C.c_void_p(r_ptr), C.c_void_p(s_ptr), int(bool(auto_reset))))
+                                  C.c_void_p(r_ptr), C.c_void_p(s_ptr), int(bool(auto_reset)), _stream(self.device)))
 
     def generate_rollouts(self, actions=None, test=False):
         """RolloutStudent.generate_rollouts (rollout.py:75-172) for open-loop actions [T, B, 4] (None: the env's
@@ -215,11 +221,63 @@ class VecBlocksEnv:
         if actions is not None:
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
             assert actions.shape == (T, B, 4), actions.shape
-        ep = dict(o=self._empty(B, T + 1, self.dimo), u=self._empty(B, T, 4), g=self._empty(B, T, self.dimg),
-                  ag=self._empty(B, T + 1, self.dimg), info_is_success=self._empty(B, T, 1), r=self._empty(B, T))
+        ep = self._episode_tensors()
         check(self.L.bp_rollout(self._h, _ptr(actions), int(bool(test)), _ptr(ep["o"]), _ptr(ep["ag"]), _ptr(ep["g"]),
                                 _ptr(ep["u"]), _ptr(ep["info_is_success"]), _ptr(ep["r"]), _stream(self.device)))
         return ep
+
+    def _episode_tensors(self):
+        B, T = self.num_envs, MAX_EPISODE_STEPS
+        return dict(o=self._empty(B, T + 1, self.dimo), u=self._empty(B, T, 4), g=self._empty(B, T, self.dimg),
+                    ag=self._empty(B, T + 1, self.dimg), info_is_success=self._empty(B, T, 1), r=self._empty(B, T))
+
+    def rollout_begin(self, ep, test=False, g0=None):
+        """reset_all_rollouts (rollout.py:48-64) into slot 0 of the episode tensors `ep` (see generate_rollouts)."""
+        check(self.L.bp_rollout_begin(self._h, int(bool(test)), _ptr(ep["o"]), _ptr(ep["ag"]), _ptr(g0), _stream(self.device)))
+
+    def rollout_step(self, ep, t, actions):
+        """One step of every env on `actions` [B, 4] (the policy's u_t): slot t + 1 of o / ag, slot t of g / u / ..."""
+        assert actions.is_cuda and actions.dtype == torch.float32 and actions.is_contiguous() and tuple(actions.shape) == (self.num_envs, 4)
+        check(self.L.bp_rollout_step(self._h, int(t), _ptr(actions), _ptr(ep["o"]), _ptr(ep["ag"]), _ptr(ep["g"]), _ptr(ep["u"]),
+                                     _ptr(ep["info_is_success"]), _ptr(ep["r"]), _stream(self.device)))
+
+    def collect_rollouts(self, policy, test=False, graph=False):
+        """RolloutStudent.generate_rollouts (rollout.py:75-172) CLOSED-LOOP for the whole batch: `policy(o, ag, g)`
+        -- the stand-in for policy.get_actions (rollout.py:92-97) -- maps CUDA tensors o [B, dimo], ag [B, dimg],
+        g [B, dimg] to actions [B, 4] at every one of the T = 50 steps; the episode comes back batch-major exactly as
+        convert_episode_to_batch_major (util.py:118-128) lays it out.  One reset launch + one step launch per step,
+        no host synchronisation; graph=True captures the 50-step loop (policy included) in a CUDA graph on first use
+        and replays it afterwards (the policy must then be capturable: static shapes, no host syncs)."""
+        T = MAX_EPISODE_STEPS
+        if graph:
+            key = (id(policy), bool(test))
+            cache = self.__dict__.setdefault("_graphs", {})
+            if key not in cache:
+                ep = self._episode_tensors()
+                g0 = self._empty(self.num_envs, self.dimg)
+                state = self.get_state()                                   # warm-up and capture must not consume episodes
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    self._collect(policy, ep, g0, test)                    # warm-up (lazy module init, cudaFuncSetAttribute)
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    self._collect(policy, ep, g0, test)
+                self.set_state(state)
+                cache[key] = (gr, ep)
+            gr, ep = cache[key]
+            gr.replay()
+            return {k: v.clone() for k, v in ep.items()}
+        ep = self._episode_tensors()
+        self._collect(policy, ep, self._empty(self.num_envs, self.dimg), test)
+        return ep
+
+    def _collect(self, policy, ep, g0, test):
+        self.rollout_begin(ep, test=test, g0=g0)
+        for t in range(MAX_EPISODE_STEPS):
+            u = policy(ep["o"][:, t], ep["ag"][:, t], g0)
+            self.rollout_step(ep, t, u.to(torch.float32).contiguous())
 
     def goal(self):
         """desired_goal rows [B, dimg]: fixed per env id (colours are fixed lists, fetch_env.py:260-273)."""
@@ -265,11 +323,14 @@ class VecBlocksEnv:
         torch.cuda.current_stream(self.device).synchronize()
 
     def stats_tensor(self):
-        """float64[8] device tensor aliasing the handle's statistics vector (all-reduce it in place)."""
+        """float64[8] device tensor ALIASING the handle's statistics vector (all-reduce it in place).  It is a view
+        into memory the handle owns: it dangles after close(); take .clone() to keep the numbers."""
+        if not getattr(self, "_h", None):
+            raise _lib.BlockPuzzleError("the env has been closed")
         return _wrap_device_f64(self._stats_ptr, _lib.BP_NUM_STATS, self.device)
 
     def stats(self):
-        v = self.stats_tensor().cpu().numpy()
+        v = self.stats_tensor().cpu().numpy()          # .cpu() copies: nothing aliasing the handle escapes
         return {k: float(v[i]) for i, k in enumerate(_lib.STAT_NAMES)}
 
     def stats_reset(self):
@@ -343,7 +404,10 @@ class GymBlocksEnv:
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 25}
     reward_range = (-float("inf"), float("inf"))
 
-    def __init__(self, env_name, device=None, seed=0):
+    def __init__(self, env_name, device=None, seed=0, reward_type="sparse"):
+        # reward_type: the registered kwarg (gym_blocks/__init__.py:9 ...); the reference stores it and never reads
+        # it (fetch_env.py:72, appendix A8)
+        self.reward_type = reward_type
         self._vec = VecBlocksEnv(env_name, 1, device=device, seed=seed)
         self.spec_id = env_name
         self._max_episode_steps = MAX_EPISODE_STEPS
@@ -353,7 +417,12 @@ class GymBlocksEnv:
         self.unwrapped = self
 
     def _obs(self, d):
-        return {k: v[0].double().cpu().numpy() for k, v in d.items()}
+        o = {k: v[0].double().cpu().numpy() for k, v in d.items()}
+        if self._vec.env_name != "BlocksTouchVariation-v0":
+            # _sample_goal builds the goal from python ints (fetch_env.py:260-273): int64; Variation pads into a
+            # float array (:682-695)
+            o["desired_goal"] = o["desired_goal"].astype(np.int64)
+        return o
 
     def seed(self, seed=None):
         return self._vec.seed(seed)

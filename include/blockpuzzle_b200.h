@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define BP_ABI_VERSION 1
+#define BP_ABI_VERSION 2   /* 2: bp_step_host takes the caller's stream; bp_rollout_begin / bp_rollout_step; BP_ERR_NO_ATTRIBUTE */
 
 typedef enum {
     BP_OK = 0,
@@ -130,9 +130,11 @@ int bp_step(bp_handle* h, const float* d_actions, int K, float* d_obs, float* d_
 /* Same call with HOST buffers (pinned or pageable): actions are copied to the
  * device, outputs copied back, chunked over envs and double-buffered on two
  * internal streams.  Synchronous.  This is the end-to-end path a CPU trainer
- * (rollout.py:121-131) uses. */
+ * (rollout.py:121-131) uses.  `stream` is the stream the caller queued its
+ * earlier calls on this handle on (bp_seed / bp_reset / bp_set_state / bp_step):
+ * the internal streams wait for it before the first copy. */
 int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, float* h_ag,
-                 float* h_reward, float* h_success, int auto_reset);
+                 float* h_reward, float* h_success, int auto_reset, void* stream);
 
 /* RolloutStudent.generate_rollouts (rollout.py:75-172) for open-loop actions, with the per-env loop
  * (rollout.py:121-131) and convert_episode_to_batch_major (util.py:118-128) fused into the step
@@ -143,6 +145,19 @@ int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, floa
  * d_g, d_u, d_success, d_reward may be NULL.  No auto-reset: the episode ends at T. */
 int bp_rollout(bp_handle* h, const float* d_actions, int test, float* d_o, float* d_ag, float* d_g, float* d_u,
                float* d_success, float* d_reward, void* stream);
+
+/* The same collector CLOSED-LOOP: RolloutStudent asks the policy for u_t = policy.get_actions(o_t, ag_t, g) at every
+ * one of the T steps (rollout.py:91-97), so the actions cannot be known up front.
+ *   bp_rollout_begin  = reset_all_rollouts (rollout.py:48-64; + set_test() when `test`): writes slot 0 of
+ *                       d_o [B][T+1][dimo] / d_ag [B][T+1][dimg] and the goal rows d_g0 [B][dimg] (nullable);
+ *   bp_rollout_step t = one env step of every env on d_actions [B][4] (the policy's output for slot t): writes slot
+ *                       t + 1 of d_o / d_ag and slot t of d_g [B][T][dimg], d_u [B][T][4], d_success [B][T],
+ *                       d_reward [B][T] (each nullable) -- the same batch-major episode bp_rollout produces.
+ * One launch per step on `stream`, no host synchronisation: the T-step loop (policy included) can be captured in a
+ * CUDA graph.  t must run 0, 1, ..., T - 1 after a bp_rollout_begin. */
+int bp_rollout_begin(bp_handle* h, int test, float* d_o, float* d_ag, float* d_g0, void* stream);
+int bp_rollout_step(bp_handle* h, int t, const float* d_actions, float* d_o, float* d_ag, float* d_g, float* d_u,
+                    float* d_success, float* d_reward, void* stream);
 
 /* BlocksTouchEnv.set_test / BlocksTouchChooseEnv.set_test / Variation.set_test
  * (fetch_env.py:365-368, 443-446, 641-644); BP_ERR_NOT_IMPLEMENTED for

@@ -1,8 +1,9 @@
 """Builds oracle/_ref/: the reference's own code, compiled, so that it travels to the GPU box (TEST INFRASTRUCTURE).
 
 /root/reference exists only in the build container.  This recipe byte-compiles the reference's Python
-modules *from where they lie* into sourceless `.pyc` files under oracle/_ref/gym_blocks/ (CPython imports a
-`foo.pyc` sitting where `foo.py` would be) and stores, under the MJCF scene names the reference asks for
+modules *from where they lie* into sourceless bytecode files under oracle/_ref/gym_blocks/ (extension `.pyb`:
+the snapshot that travels to the GPU box drops `*.pyc`; oracle/refharness installs an import finder that loads
+them with importlib's SourcelessFileLoader) and stores, under the MJCF scene names the reference asks for
 (robot_env.py:20, fetch_env.py:528-530,549), the JSON model digests oracle/refharness/mjcf.py extracts from
 the real XML -- the fake `mujoco_py.load_model_from_path` accepts either form.
 
@@ -17,6 +18,7 @@ import os
 import py_compile
 import shutil
 import sys
+import warnings
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(_HERE))
@@ -24,6 +26,7 @@ from oracle.refharness import mjcf  # noqa: E402
 
 SRC = "/root/reference"
 OUT = os.path.join(_HERE, "_ref")
+EXT = ".pyb"
 
 # the modules the replay harness imports (env hot path + its callers); trainers, networks, plotting and the
 # CLI are out of scope and are not compiled
@@ -48,13 +51,15 @@ def build(src=SRC, out=OUT):
         shutil.rmtree(out)
     for rel in MODULES:
         s = os.path.join(src, rel)
-        d = os.path.join(out, rel[:-3] + ".pyc")
+        d = os.path.join(out, rel[:-3] + EXT)
         os.makedirs(os.path.dirname(d), exist_ok=True)
         # dfile = the reference-relative name: tracebacks cite gym_blocks/envs/fetch_env.py:<line>
-        py_compile.compile(s, cfile=d, dfile=rel, doraise=True, optimize=0,
-                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", SyntaxWarning)      # `is not ''` in the reference's logs() helpers
+            py_compile.compile(s, cfile=d, dfile=rel, doraise=True, optimize=0,
+                               invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
     # gym_blocks/policy_gradient has no __init__.py upstream (it is run as scripts); the harness loads
-    # policy_gradient/rollout.pyc by path
+    # policy_gradient/rollout by path
     for rel in SCENES:
         digest = mjcf.digest_from_xml(os.path.join(src, "gym_blocks", "envs", "assets", rel))
         d = os.path.join(out, "gym_blocks", "envs", "assets", rel)

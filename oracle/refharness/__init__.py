@@ -39,7 +39,7 @@ def reference_root():
         return forced if os.path.isdir(os.path.join(forced, "gym_blocks")) else None
     if os.path.isdir(os.path.join(REF_SOURCE, "gym_blocks")):
         return REF_SOURCE
-    if os.path.isdir(os.path.join(REF_COMPILED, "gym_blocks")):
+    if os.path.exists(os.path.join(REF_COMPILED, "gym_blocks", "__init__" + ".pyb")):
         return REF_COMPILED
     return None
 
@@ -76,6 +76,30 @@ class _NumpyProxy(object):
         return getattr(self._real, name)
 
 
+COMPILED_EXT = ".pyb"
+
+
+class _CompiledReferenceFinder(object):
+    """Import finder for oracle/_ref: `gym_blocks[.x.y]` -> the sourceless bytecode files oracle/build_ref.py wrote."""
+
+    def __init__(self, root):
+        self.root = root
+
+    def find_spec(self, name, path=None, target=None):
+        import importlib.machinery
+        import importlib.util
+        if name != "gym_blocks" and not name.startswith("gym_blocks."):
+            return None
+        rel = os.path.join(self.root, *name.split("."))
+        pkg, mod = os.path.join(rel, "__init__" + COMPILED_EXT), rel + COMPILED_EXT
+        if os.path.exists(pkg):
+            return importlib.util.spec_from_file_location(name, pkg, loader=importlib.machinery.SourcelessFileLoader(name, pkg),
+                                                          submodule_search_locations=[rel])
+        if os.path.exists(mod):
+            return importlib.util.spec_from_file_location(name, mod, loader=importlib.machinery.SourcelessFileLoader(name, mod))
+        return None
+
+
 def activate(root=None):
     """Make `import gym_blocks` resolve to the unmodified reference under the stub packages."""
     if _state["root"] is not None:
@@ -84,9 +108,12 @@ def activate(root=None):
     if root is None:
         raise RuntimeError("neither /root/reference nor oracle/_ref is present: run oracle/build_ref.py where the reference exists")
     repo = os.path.dirname(_ORACLE)
-    for p in (repo, STUBS, root):
+    compiled = not os.path.exists(os.path.join(root, "gym_blocks", "__init__.py"))
+    for p in (repo, STUBS) + (() if compiled else (root,)):
         if p not in sys.path:
             sys.path.append(p)
+    if compiled and not any(isinstance(f, _CompiledReferenceFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _CompiledReferenceFinder(root))   # ahead of PathFinder, which would see namespace packages
     import gym
     assert gym.__version__.endswith("-stub"), "a real gym shadows the replay stubs"
     import gym_blocks  # noqa: F401  registers the seven ids (gym_blocks/__init__.py:6-53)
@@ -176,9 +203,13 @@ def callers():
     import gym_blocks.config as cfg
     name = "gym_blocks_policy_gradient_rollout"
     if name not in sys.modules:
+        import importlib.machinery
         base = os.path.join(root, "gym_blocks", "policy_gradient", "rollout")
-        path = base + ".py" if os.path.exists(base + ".py") else base + ".pyc"
-        spec = importlib.util.spec_from_file_location(name, path)
+        if os.path.exists(base + ".py"):
+            spec = importlib.util.spec_from_file_location(name, base + ".py")
+        else:
+            spec = importlib.util.spec_from_file_location(name, base + COMPILED_EXT,
+                                                          loader=importlib.machinery.SourcelessFileLoader(name, base + COMPILED_EXT))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         sys.modules[name] = mod

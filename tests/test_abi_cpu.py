@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.load()  # resolves each symbol; raises if one is missing
     for name in declared:
         assert hasattr(L, name)
-    assert L.bp_abi_version() == 1
+    assert L.bp_abi_version() == 2
 
 
 def test_env_table_through_the_abi():

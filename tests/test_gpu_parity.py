@@ -270,6 +270,112 @@ def test_step_host_matches_device_path():
     assert e1.get_state().tobytes() == e2.get_state().tobytes()
 
 
+@pytest.mark.parametrize("name,B,K", [("ToppleTower-v0", 1, 1), ("ToppleTower-v0", 1001, 3), ("BlocksTouchVariation-v0", 1, 1),
+                                      ("BlocksTouchVariation-v0", 1003, 5), ("GripperTouch-v0", 131, 3), ("BlocksTouchChoose-v0", 257, 1)])
+def test_step_host_odd_sizes_keep_the_row_stores_aligned(name, B, K):
+    """the staged sub-buffers of bp_step_host start on 16 bytes for every (id, B, K) -- ToppleTower /
+    Variation rows (dimo 70 / 87, dimg 36) used to leave d_ag misaligned for odd K*n and fault in the float4 stores."""
+    import blockpuzzle_gym_b200 as bpg
+    a = np.random.RandomState(4).uniform(-1, 1, size=(K, B, 4)).astype(np.float32)
+    e1 = bpg.make_vec(name, B, device=0, seed=9); e1.reset()
+    e2 = bpg.make_vec(name, B, device=0, seed=9); e2.reset()
+    d = e1.step_fused(torch.from_numpy(a).cuda(), auto_reset=True)
+    h = e2.step_host(a, auto_reset=True)
+    for k in ("observation", "achieved_goal", "reward", "is_success"):
+        assert np.array_equal(d[k].cpu().numpy(), h[k]), k
+    assert e1.get_state().tobytes() == e2.get_state().tobytes()
+
+
+def test_step_host_is_ordered_after_the_callers_stream():
+    """reset() queued on the caller's stream, step_host() right behind it on the library's private
+    streams -- the step kernel must see the reset state (no synchronising call in between)."""
+    import blockpuzzle_gym_b200 as bpg
+    B, K = 200000, 2
+    a = np.random.RandomState(5).uniform(-1, 1, size=(K, B, 4)).astype(np.float32)
+    e1 = bpg.make_vec("BlocksTouch-v0", B, device=0, seed=2)
+    e2 = bpg.make_vec("BlocksTouch-v0", B, device=0, seed=2)
+    da = torch.from_numpy(a).cuda()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            e2.reset()                      # asynchronous launches on `side`; the last one defines the state
+        h = e2.step_host(a, auto_reset=True)
+    for _ in range(3):
+        e1.reset()
+    d = e1.step_fused(da, auto_reset=True)
+    for k in ("observation", "achieved_goal", "reward", "is_success"):
+        assert np.array_equal(d[k].cpu().numpy(), h[k]), k
+
+
+def test_step_counter_saturates_instead_of_wrapping():
+    """with auto_reset = 0 the packed 8-bit step counter used to wrap at 256 into the success bit."""
+    import blockpuzzle_gym_b200 as bpg
+    env = bpg.make_vec("BlocksTouch-v0", 64, device=0, seed=1); env.reset()
+    a = torch.zeros(300, 64, 4, device="cuda")
+    out = env.step_fused(a, auto_reset=False, want_done=True)
+    done = out["done"].cpu().numpy()
+    assert not done[:49].any() and done[49:].all()              # TimeLimit keeps done = True past T
+    assert (out["is_success"].cpu().numpy() == 0).all()         # nothing touched: the latch never sets
+    assert (env.get_state()["t"] == 255).all()
+
+
+def test_entry_points_leave_the_current_device_alone():
+    import blockpuzzle_gym_b200 as bpg
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    env = bpg.make_vec("BlocksTouch-v0", 256, device=1, seed=1)
+    env.reset(); env.step_fused(None, K=3); env.get_state()
+    assert torch.cuda.current_device() == 0
+    assert torch.empty(1, device="cuda").device.index == 0
+
+
+def test_step_fused_reallocates_mismatched_output_buffers():
+    import blockpuzzle_gym_b200 as bpg
+    env = bpg.make_vec("BlocksTouch-v0", 100, device=0, seed=1); env.reset()
+    out = env.step_fused(None, K=4)
+    keep = out["observation"]
+    out2 = env.step_fused(None, K=4, out=out)
+    assert out2["observation"] is keep                          # matching buffers are reused
+    out3 = env.step_fused(None, K=6, out=out)                   # a different K: fresh buffers, no out-of-bounds write
+    assert out3["observation"].shape == (6, 100, 40)
+    out3["reward"] = out3["reward"][:, ::2]                     # a sliced view is never handed to the kernel
+    out4 = env.step_fused(None, K=6, out=out3)
+    assert out4["reward"].shape == (6, 100) and out4["reward"].is_contiguous()
+
+
+@pytest.mark.parametrize("name,test", [("BlocksTouch-v0", False), ("BlocksTouchCurriculum-v0", True), ("ToppleTower-v0", False),
+                                       ("BlocksTouchVariation-v0", False)])
+def test_closed_loop_collector_matches_stepwise_oracle(name, test):
+    """SURVEY 8(f)1, closed loop (rollout.py:91-150): bp_rollout_begin + 50 x bp_rollout_step with a policy that reads
+    o_t / ag_t / g, against the oracle stepped with the same policy; and the CUDA-graph replay of the same loop."""
+    B, T = 300, 50
+    env, ref = _make(name, B, seed=21)
+    W = torch.from_numpy(np.random.RandomState(1).normal(size=(env.dimo, 4)).astype(np.float32)).cuda()
+
+    def policy(o, ag, g):
+        # quantised to a 1/8 grid so that device / host matmul rounding cannot change an action
+        return torch.round(torch.tanh(o @ W * 0.7 + (ag - g).sum(1, keepdim=True) * 0.05) * 10.0) / 8.0
+
+    for rep, graph in enumerate((False, True, True)):
+        ep = env.collect_rollouts(policy, test=test, graph=graph)
+        o, ag, g = ref.reset()
+        if test:
+            o, ag, g = ref.set_test()
+        assert np.array_equal(ep["o"][:, 0].cpu().numpy(), o) and np.array_equal(ep["ag"][:, 0].cpu().numpy(), ag)
+        for t in range(T):
+            u = policy(torch.from_numpy(o).cuda(), torch.from_numpy(ag).cuda(), torch.from_numpy(g).cuda()).cpu().numpy()
+            assert np.array_equal(ep["u"][:, t].cpu().numpy(), u), (rep, t)
+            o, ag, r, s, _, _ = ref.step(u)
+            assert np.array_equal(ep["o"][:, t + 1].cpu().numpy(), o), (rep, t)
+            assert np.array_equal(ep["ag"][:, t + 1].cpu().numpy(), ag)
+            assert np.array_equal(ep["g"][:, t].cpu().numpy(), g)
+            assert np.array_equal(ep["r"][:, t].cpu().numpy().view(np.uint32), r.view(np.uint32))
+            assert np.array_equal(ep["info_is_success"][:, t, 0].cpu().numpy(), s)
+        _assert_state_equal(env, ref, f"after rollout {rep}")
+
+
 def test_gym_single_env_surface():
     """The object the reference gets from gym.make(env_name): reset/step/compute_reward/seed + TimeLimit."""
     import blockpuzzle_gym_b200 as bpg
@@ -292,9 +398,9 @@ def test_gym_single_env_surface():
 
 
 def test_all_step_kernels_agree():
-    """The quiet path and the schedulers must be result-neutral: BP_STEP_KERNEL=simple runs the full physics
-    for every env-step in order; the two-warp (default), the warp-autonomous and the tiled kernel must leave
-    byte-identical state and outputs (checked via hashes)."""
+    """The quiet path and the scheduler must be result-neutral: BP_STEP_KERNEL=simple runs the full physics (the
+    shared-memory column form, sim_step_col) for every env-step in order; the warp-autonomous kernel (quiet path +
+    register-resident passes, sim_step_reg) must leave byte-identical state and outputs (checked via hashes)."""
     import hashlib
     import subprocess
     import sys
@@ -309,10 +415,10 @@ def test_all_step_kernels_agree():
         "print(h.hexdigest())\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for mode in ("duo", "async", "tiled", "simple"):
+    for mode in ("async", "simple"):
         env = dict(os.environ, BP_STEP_KERNEL=mode, PYTHONPATH=root)
         outs.append(subprocess.check_output([sys.executable, "-c", code], env=env, cwd=root).decode().strip().splitlines()[-1])
-    assert outs[0] == outs[1] == outs[2] == outs[3]
+    assert outs[0] == outs[1]
 
 
 @pytest.mark.parametrize("name,test", [("BlocksTouch-v0", False), ("BlocksTouchCurriculum-v0", True), ("BlocksTouchVariation-v0", False),
