@@ -914,13 +914,22 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
             // 4 [12] 3.28e9, 5 [10] 3.23e9, 6 [8] 3.08e9 env-steps/s
             // per id (E = 4 / 3 / 2): GripperTouch 3.78 / 3.97 / 3.83e9, ToppleTower 1.32 / 1.34 / 1.22e9, Variation 1.42 / 1.46 / 1.41e9
             static const int e_env = [] { const char* e = getenv("BP_ASYNC_E"); return e ? atoi(e) : 0; }();
-            const int e_sel = e_env ? e_env : ((ID == 0 || ID == 2 || ID == 6) ? 3 : kAsyncE);
-            auto go = [&](auto ec) -> int {
+            const int e_def = (ID == 0 || ID == 2 || ID == 6) ? 3 : kAsyncE;
+#ifdef BP_EXPERIMENTS
+            const int e_sel = e_env ? e_env : e_def;
+#else
+            const int e_sel = e_def;   // other E are only instantiated in the experiments build
+            (void)e_env;
+#endif
+            // the lean instantiation serves the plain fused step (see step_kernel_async)
+            const bool lean = a.layout == 0 && a.actions && !a.actions_out && !a.done && !a.goal_out && !a.reset_obs && !a.reset_ag;
+            auto go = [&](auto ec, auto lc) -> int {
                 constexpr int E = decltype(ec)::value;
+                constexpr bool LEAN = decltype(lc)::value;
                 using A = Async<ID, E>;
                 static AttrOnce once;
                 if (once.need(h->device)) {
-                    int r = set_smem_attr(step_kernel_async<ID, E>, A::SMEM + pad);
+                    int r = set_smem_attr(step_kernel_async<ID, E, LEAN>, A::SMEM + pad);
 #ifdef BP_EXPERIMENTS
                     if (r == BP_OK) r = set_smem_attr(step_kernel_duo<ID, E>, Duo<ID, E>::SMEM + pad);
 #endif
@@ -934,7 +943,7 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                     const char* r = getenv("BP_RESET_MIN"); const char* q = getenv("BP_PASS_MIN");
                     const char* fr = getenv("BP_FILL_RULE");   // margin of the fill-comparison pass trigger, -1: off
                     const int frv = fr ? atoi(fr) : 8;
-                    return (r ? atoi(r) : 4) | ((q ? atoi(q) : 32) << 8) | (frv >= 0 ? (1 << 16) | (frv << 17) : 0);   // measured: reset 1/4/8/16/32 -> 3.03/3.08/3.02/2.94/2.99e9; pass 16/24/28/32 -> 2.71/3.01/3.02/3.08e9
+                    return (r ? atoi(r) : 32) | ((q ? atoi(q) : 24) << 8) | (frv >= 0 ? (1 << 16) | (frv << 17) : 0);   // measured (round 2, lean kernel): reset 4 / 32 -> 4.33 / 4.48e9 at pass 24; pass 20 / 24 / 28 -> 4.44 / 4.48 / 4.46e9 (every reset pass streams ~12 KB of cold code through the instruction cache)
                 }();
                 for (int k0 = 0; k0 < a.K; k0 += kMaxFused) {
                     StepArgs c = a;
@@ -945,11 +954,17 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
 #ifdef BP_EXPERIMENTS
                     if (choice == 3) { step_kernel_duo<ID, E><<<nblk(a.B, A::CS), 64, Duo<ID, E>::SMEM + pad, s>>>(h->d_state, c); continue; }
 #endif
-                    step_kernel_async<ID, E><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
+                    step_kernel_async<ID, E, LEAN><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
                 }
                 return (int)BP_OK;
             };
-            int r = e_sel == 2 ? go(std::integral_constant<int, 2>()) : e_sel == 3 ? go(std::integral_constant<int, 3>()) : go(std::integral_constant<int, 4>());
+            using T_ = std::true_type; using F_ = std::false_type;
+            auto go_e = [&](auto ec) -> int { return lean ? go(ec, T_()) : go(ec, F_()); };
+#ifdef BP_EXPERIMENTS
+            int r = e_sel == 2 ? go_e(std::integral_constant<int, 2>()) : e_sel == 3 ? go_e(std::integral_constant<int, 3>()) : go_e(std::integral_constant<int, 4>());
+#else
+            int r = go_e(std::integral_constant<int, ((ID == 0 || ID == 2 || ID == 6) ? 3 : kAsyncE)>());
+#endif
             if (r != BP_OK) return r;
         }
         return (int)BP_OK;
