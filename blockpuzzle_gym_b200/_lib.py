@@ -51,6 +51,7 @@ SYMBOLS = {
     "bp_set_test": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "bp_increase_difficulty": (_i, [_vp, C.POINTER(_i)]),
     "bp_get_difficulty": (_i, [_vp, C.POINTER(_i)]),
+    "bp_set_option": (_i, [_vp, C.c_char_p, _i]),
     "bp_get_ranges": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "bp_set_ranges": (_i, [_vp, C.c_double, C.c_double]),
     "bp_get_state": (_i, [_vp, _vp, _vp]),

@@ -37,6 +37,7 @@ struct Async {
 };
 
 constexpr int kAsyncE = 4;  // envs per lane
+constexpr int kTuneForceFull = 1 << 23;   // StepArgs::tune: skip the quiet path (measurement of the all-full-physics floor)
 
 // The slab's three bookkeeping words per env: [0] touch masks (now | ever << 16), [1] kernel-private flags
 // (bit 31: cubes static, bits 0-14: their contact pairs) | env flags << 16 (t | succ << 8 | nb << 9),
@@ -198,7 +199,7 @@ __device__ __forceinline__ uint32_t try_quiet_step(uint32_t* __restrict__ st, co
     float a[4] = {a4.x, a4.y, a4.z, a4.w};
     int inv = 0;
     clip_action(a, inv);
-    if (!(priv >> 31)) return 0u;
+    if (!(priv >> 31) || (p.tune & kTuneForceFull)) return 0u;
     Grip g2;
 #pragma unroll
     for (int d = 0; d < 3; ++d) { g2.g[d] = s_grp[d * CS + w]; g2.gv[d] = s_grp[(3 + d) * CS + w]; }

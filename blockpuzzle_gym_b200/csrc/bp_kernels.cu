@@ -838,6 +838,7 @@ struct bp_handle {
     float* d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
     cudaEvent_t ev = nullptr;       // orders the staging streams after the caller's stream
+    int force_full = 0;             // bp_set_option("force_full_physics"): every env-step takes the full-physics pass
 };
 
 static Ranges ranges_of(const bp_handle* h) {
@@ -947,7 +948,7 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                 }();
                 for (int k0 = 0; k0 < a.K; k0 += kMaxFused) {
                     StepArgs c = a;
-                    c.tune = tune;
+                    c.tune = tune | (h->force_full ? kTuneForceFull : 0);
                     c.K = (a.K - k0) < kMaxFused ? (a.K - k0) : kMaxFused;
                     c.k0 = a.k0 + k0;
                     c.act_k0 = a.act_k0 + k0;
@@ -1275,6 +1276,12 @@ int bp_increase_difficulty(bp_handle* h, int* max_reached) {
     }
     if (max_reached) *max_reached = ret;
     return BP_OK;
+}
+
+int bp_set_option(bp_handle* h, const char* name, int value) {
+    if (!h || !name) return fail(BP_ERR_INVALID_ARG, "null argument");
+    if (strcmp(name, "force_full_physics") == 0) { h->force_full = value != 0; return BP_OK; }
+    return fail(BP_ERR_INVALID_ARG, std::string("unknown option ") + name);
 }
 
 int bp_get_difficulty(const bp_handle* h, int* difficulty) {

@@ -302,6 +302,10 @@ class VecBlocksEnv:
         check(self.L.bp_get_difficulty(self._h, C.byref(r)))
         return r.value
 
+    def set_option(self, name, value):
+        """Measurement knobs of the library (bp_set_option), e.g. "force_full_physics"."""
+        check(self.L.bp_set_option(self._h, name.encode(), int(value)))
+
     def get_ranges(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         check(self.L.bp_get_ranges(self._h, C.byref(a), C.byref(b), C.byref(c)))

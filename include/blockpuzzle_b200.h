@@ -170,6 +170,9 @@ int bp_set_test(bp_handle* h, float* d_obs, float* d_ag, float* d_g, void* strea
  * (BlocksTouchChoose-v0 without curriculum: obj_range_step is never set, fetch_env.py:413-415,420). */
 int bp_increase_difficulty(bp_handle* h, int* max_reached);
 int bp_get_difficulty(const bp_handle* h, int* difficulty);           /* fetch_env.py:96-97 */
+/* measurement knobs (no reference counterpart).  "force_full_physics" != 0: every env-step runs the complete
+ * BlockPhys step (no quiet path) -- results are identical, only slower: the floor bench.py reports. */
+int bp_set_option(bp_handle* h, const char* name, int value);
 /* direct access to the curriculum knobs (obj_range, wrong_obj_range, max_obj_range) */
 int bp_get_ranges(const bp_handle* h, double* obj_range, double* wrong_obj_range, double* max_obj_range);
 int bp_set_ranges(bp_handle* h, double obj_range, double wrong_obj_range);

@@ -376,6 +376,47 @@ def test_closed_loop_collector_matches_stepwise_oracle(name, test):
         _assert_state_equal(env, ref, f"after rollout {rep}")
 
 
+def test_scripted_push_policy_at_scale_matches_oracle():
+    """the GPU parity suite must also see a policy that really pushes cubes.  4096 envs
+    driven closed-loop by bench.py's scripted push policy (move behind cube 0, descend, push it into cube 1); the C
+    oracle replays the recorded actions: every observation, touch matrix, reward and latch bit-identical, and the
+    workload is contact-heavy (most episodes succeed, the full-physics share is well above the random-action one)."""
+    import bench
+    B, T = 4096, 50
+    env, ref = _make("BlocksTouch-v0", B, seed=77)
+    env.stats_reset()
+    ep = env.collect_rollouts(bench.push_policy([0]))
+    st = env.stats()
+    u = ep["u"].cpu().numpy()
+    o, ag, g = ref.reset()
+    assert np.array_equal(ep["o"][:, 0].cpu().numpy(), o)
+    succ_any = np.zeros(B, bool)
+    for t in range(T):
+        o, ag, r, s, _, _ = ref.step(u[:, t])
+        assert np.array_equal(ep["o"][:, t + 1].cpu().numpy(), o), t
+        assert np.array_equal(ep["ag"][:, t + 1].cpu().numpy(), ag), t
+        assert np.array_equal(ep["r"][:, t].cpu().numpy().view(np.uint32), r.view(np.uint32)), t
+        assert np.array_equal(ep["info_is_success"][:, t, 0].cpu().numpy(), s), t
+        succ_any |= s != 0
+    _assert_state_equal(env, ref, "after the scripted episode")
+    assert succ_any.mean() > 0.6, succ_any.mean()                   # the policy does make the cubes touch
+    assert st["worker_steps"] / st["steps"] > 0.18                  # and needs the full physics far more often than random actions (0.13)
+    # the same episode replayed as one fused launch (what bench.py times) gives the same final state
+    env2, _ = _make("BlocksTouch-v0", B, seed=77)
+    env2.reset()
+    out = env2.step_fused(ep["u"].transpose(0, 1).contiguous(), auto_reset=False)
+    assert np.array_equal(out["observation"][-1].cpu().numpy(), o)
+    assert env2.get_state().tobytes() == env.get_state().tobytes()
+    # forcing the full physics everywhere changes nothing but the speed
+    env3, _ = _make("BlocksTouch-v0", B, seed=77)
+    env3.set_option("force_full_physics", 1)
+    env3.reset(); env3.stats_reset()
+    out3 = env3.step_fused(ep["u"].transpose(0, 1).contiguous(), auto_reset=False)
+    assert env3.stats()["worker_steps"] == env3.stats()["steps"] == B * T
+    for k in ("observation", "achieved_goal", "reward", "is_success"):
+        assert torch.equal(out[k], out3[k]), k
+
+
 def test_gym_single_env_surface():
     """The object the reference gets from gym.make(env_name): reset/step/compute_reward/seed + TimeLimit."""
     import blockpuzzle_gym_b200 as bpg
