@@ -439,9 +439,10 @@ def test_gym_single_env_surface():
 
 
 def test_all_step_kernels_agree():
-    """The quiet path and the scheduler must be result-neutral: BP_STEP_KERNEL=simple runs the full physics (the
-    shared-memory column form, sim_step_col) for every env-step in order; the warp-autonomous kernel (quiet path +
-    register-resident passes, sim_step_reg) must leave byte-identical state and outputs (checked via hashes)."""
+    """The quiet path and the schedulers must be result-neutral: BP_STEP_KERNEL=simple runs the full physics (the
+    shared-memory column form, sim_step_col) for every env-step in order; the step-synchronous kernels (split: quiet
+    kernel + compacted full-physics kernel + reset kernel per step, the default) and the warp-autonomous slab kernel
+    (async) must leave byte-identical state and outputs (checked via hashes)."""
     import hashlib
     import subprocess
     import sys
@@ -456,10 +457,10 @@ def test_all_step_kernels_agree():
         "print(h.hexdigest())\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
-    for mode in ("async", "simple"):
+    for mode in ("split", "async", "simple"):
         env = dict(os.environ, BP_STEP_KERNEL=mode, PYTHONPATH=root)
         outs.append(subprocess.check_output([sys.executable, "-c", code], env=env, cwd=root).decode().strip().splitlines()[-1])
-    assert outs[0] == outs[1]
+    assert outs[0] == outs[1] == outs[2]
 
 
 @pytest.mark.parametrize("name,test", [("BlocksTouch-v0", False), ("BlocksTouchCurriculum-v0", True), ("BlocksTouchVariation-v0", False),
