@@ -31,9 +31,14 @@ struct Async {
     static constexpr int NB = C::NB;
     static constexpr int CS = 32 * E;                       // envs per warp = column stride of the slab
     static constexpr int W_CUB = 9 * NB * CS, W_GRP = 10 * CS, W_MSC = 3 * CS;
+    // ids with three or four cubes keep round 1's pass (cubes stepped in place in the slab through shared-memory
+    // loops, 4 words of per-lane scratch per cube): unrolled over 4 cubes, 8 finger slots and 6 pairs the register
+    // form is 74-91 KB of SASS and measured 13-23 % slower there (ToppleTower 1.32 -> 1.01e9, Variation 1.41 -> 1.22e9)
+    static constexpr bool REG_PASS = NB <= 2;
+    static constexpr int W_COL = REG_PASS ? 0 : Col<NB, CS, 32>::kScratch * 32;
     static constexpr int W_PEND = CS;                        // two uint16 rings of CS entries: pending full-physics env-steps, pending resets
     static constexpr int W_BITS = kMaxFused * E;             // reward bits of every (step, env) of the launch
-    static constexpr size_t SMEM = sizeof(uint32_t) * (size_t)(W_CUB + W_GRP + W_MSC + W_PEND + W_BITS);
+    static constexpr size_t SMEM = sizeof(uint32_t) * (size_t)(W_CUB + W_GRP + W_MSC + W_COL + W_PEND + W_BITS);
 };
 
 constexpr int kAsyncE = 4;  // envs per lane
@@ -241,7 +246,7 @@ __device__ __forceinline__ uint32_t try_quiet_step(uint32_t* __restrict__ st, co
 // (sim_step_reg) and written back to the slab column.
 template <int ID, int E, bool LEAN>
 __device__ __forceinline__ uint32_t full_step_item(uint32_t* __restrict__ st, const StepArgs& p, int64_t li, int pw, int k,
-                                               float* s_cub, float* s_grp, uint32_t* s_msc,
+                                               float* s_scr, float* s_cub, float* s_grp, uint32_t* s_msc,
                                                uint32_t* s_bits, WarpStats& ws) {
     using C = Cfg<ID>;
     constexpr int NB = C::NB, CS = 32 * E;
@@ -255,19 +260,24 @@ __device__ __forceinline__ uint32_t full_step_item(uint32_t* __restrict__ st, co
     for (int d = 0; d < 3; ++d) { g.g[d] = s_grp[d * CS + pw]; g.gv[d] = s_grp[(3 + d) * CS + pw]; }
     g.q[0] = s_grp[6 * CS + pw]; g.q[1] = s_grp[7 * CS + pw]; g.qv[0] = s_grp[8 * CS + pw]; g.qv[1] = s_grp[9 * CS + pw];
     uint32_t contacts = 0;
-    CubeRegs<NB> q;
+    bool is_static;
+    if constexpr (Async<ID, E>::REG_PASS) {
+        CubeRegs<NB> q;
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const float* bb = s_cub + (9 * b) * CS + pw;
-        q.x[b] = bb[0]; q.y[b] = bb[CS]; q.z[b] = bb[2 * CS]; q.c[b] = bb[3 * CS]; q.s[b] = bb[4 * CS];
-        q.vx[b] = bb[5 * CS]; q.vy[b] = bb[6 * CS]; q.vz[b] = bb[7 * CS]; q.w[b] = bb[8 * CS];
-    }
-    const bool is_static = sim_step_reg<NB, C::BG, C::VAR>(g, a, q, (int)((flags >> 9) & 7u), contacts);
+        for (int b = 0; b < NB; ++b) {
+            const float* bb = s_cub + (9 * b) * CS + pw;
+            q.x[b] = bb[0]; q.y[b] = bb[CS]; q.z[b] = bb[2 * CS]; q.c[b] = bb[3 * CS]; q.s[b] = bb[4 * CS];
+            q.vx[b] = bb[5 * CS]; q.vy[b] = bb[6 * CS]; q.vz[b] = bb[7 * CS]; q.w[b] = bb[8 * CS];
+        }
+        is_static = sim_step_reg<NB, C::BG, C::VAR>(g, a, q, (int)((flags >> 9) & 7u), contacts);
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        float* bb = s_cub + (9 * b) * CS + pw;
-        bb[0] = q.x[b]; bb[CS] = q.y[b]; bb[2 * CS] = q.z[b]; bb[3 * CS] = q.c[b]; bb[4 * CS] = q.s[b];
-        bb[5 * CS] = q.vx[b]; bb[6 * CS] = q.vy[b]; bb[7 * CS] = q.vz[b]; bb[8 * CS] = q.w[b];
+        for (int b = 0; b < NB; ++b) {
+            float* bb = s_cub + (9 * b) * CS + pw;
+            bb[0] = q.x[b]; bb[CS] = q.y[b]; bb[2 * CS] = q.z[b]; bb[3 * CS] = q.c[b]; bb[4 * CS] = q.s[b];
+            bb[5 * CS] = q.vx[b]; bb[6 * CS] = q.vy[b]; bb[7 * CS] = q.vz[b]; bb[8 * CS] = q.w[b];
+        }
+    } else {
+        is_static = sim_step_col<NB, CS, C::BG>(g, a, Col<NB, CS, 32>(s_cub + pw, s_scr), (int)((flags >> 9) & 7u), contacts);
     }
 #pragma unroll
     for (int d = 0; d < 3; ++d) { s_grp[d * CS + pw] = g.g[d]; s_grp[(3 + d) * CS + pw] = g.gv[d]; }
@@ -399,9 +409,10 @@ __global__ void __launch_bounds__(32, E == 4 ? 12 : (E == 3 ? 15 : 20)) step_ker
     float* s_cub = reinterpret_cast<float*>(smem);                    // [9*NB][CS]
     float* s_grp = s_cub + A::W_CUB;                                  // [10][CS]
     uint32_t* s_msc = reinterpret_cast<uint32_t*>(s_grp + A::W_GRP);  // [3][CS]: touch, priv | flags, status
-    uint16_t* s_pend = reinterpret_cast<uint16_t*>(s_msc + A::W_MSC); // [CS] ring: env-steps waiting for a full-physics pass
+    float* s_col = reinterpret_cast<float*>(s_msc + A::W_MSC);        // [4*NB][32] per-lane substep scratch (ids with > 2 cubes only)
+    uint16_t* s_pend = reinterpret_cast<uint16_t*>(s_col + A::W_COL); // [CS] ring: env-steps waiting for a full-physics pass
     uint16_t* s_rset = s_pend + CS;                                    // [CS] ring: envs waiting for their reset
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_msc + A::W_MSC) + A::W_PEND;  // [K][E]: reward-fail masks over 32 envs
+    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_col + A::W_COL) + A::W_PEND;  // [K][E]: reward-fail masks over 32 envs
 
     const int lane = threadIdx.x;
     const int64_t wbase = (int64_t)blockIdx.x * CS;  // launch-local index of the warp's env 0
@@ -461,7 +472,7 @@ __global__ void __launch_bounds__(32, E == 4 ? 12 : (E == 3 ? 15 : 20)) step_ker
             if (lane < take) {
                 pw = s_pend[ring(pend_head + lane)];
                 const int k = (int)(s_msc[2 * CS + pw] & 0xffffu);
-                const uint32_t code = full_step_item<ID, E, LEAN>(st, p, wbase + pw, pw, k, s_cub, s_grp, s_msc, s_bits, ws);
+                const uint32_t code = full_step_item<ID, E, LEAN>(st, p, wbase + pw, pw, k, s_col + lane, s_cub, s_grp, s_msc, s_bits, ws);
                 rs = p.auto_reset && (code & 2u);
                 s_msc[2 * CS + pw] = (uint32_t)(k + 1) | (rs ? kPendingBit : 0u);  // clears the pending flag unless a reset is due
             }
