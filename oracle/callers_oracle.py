@@ -10,7 +10,10 @@ neither vendored nor installed here).  They restate the published algorithm and 
 reference's own call sites (config.py:107-123, ddpg.py:100-120, 158-190, 214-222).  The reference's
 random draws (np.random.randint / uniform) are replaced by one Philox4x32-10 block per transition, stream 3,
 exactly as oracle/blockphys_oracle.c: bpo_her_relabel does, so the device sampler can be replayed.
-`discounted_returns` and `trim` follow in-tree code (policy_gradient/rollout.py) line by line.
+`discounted_returns` and `trim` follow in-tree code (policy_gradient/rollout.py) line by line and are PINNED to it:
+tests/test_ref_callers_cpu.py runs the reference's own policy-gradient RolloutStudent (its return accumulation) and
+calls its `trim` from source, bit for bit; the episode-batch layout is pinned to the reference's RolloutStudent +
+convert_episode_to_batch_major run unmodified, and `compute_reward` to BlocksEnv.compute_reward called directly.
 """
 import numpy as np
 

@@ -1,7 +1,10 @@
 """Single-env Python restatement of the reference step loop -- CPU ORACLE, test infrastructure only.
 
-PARITY STATUS: "parity unpinned" for the dynamics slot (MuJoCo is absent from the
-reference tree and from this image; the reference has no tests or golden vectors).
+PARITY STATUS: the reference-owned logic restated here is PINNED to the reference's own code through the C
+restatement: oracle/refharness runs the unmodified reference (stub gym / mujoco_py, BlockPhys in the MjSim
+slot), tests/test_ref_pin.py holds the C oracle to its traces bit for bit, and tests/test_oracle_cpu.py holds this
+module to the C oracle bit for bit.  The dynamics slot itself stays "own spec" (MuJoCo is absent from the
+reference tree and from this image).
 
 Structure follows the reference one function at a time (paths relative to
 /root/reference/gym_blocks), with its own numpy-float32 arithmetic, and plugs the
@@ -18,7 +21,8 @@ plays in the reference) into the `sim` slot:
     increase_difficulty / set_test      envs/fetch_env.py:351-368, 419-446, 623-644
     constructor constants               envs/tasks.py:4-144, __init__.py:6-53
 
-It is also the timed "reference-style single-env Python step loop" of BASELINE.md section 3.
+(bench.py's CPU legs time the reference itself -- oracle/refharness -- and fall back to this module only where
+neither /root/reference nor oracle/_ref exists.)
 The env-level C oracle (bpo_env_*) restates the same logic independently;
 tests/test_oracle_cpu.py checks the two agree bit for bit.
 """
