@@ -424,7 +424,7 @@ def run_ours(args):
     avail = _mem_available_gb()
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     e2e_note = None
-    while Ke > 8 and avail is not None and per_call_gb * local_world * 1.5 > avail:
+    while Ke > 8 and avail is not None and per_call_gb * local_world > 0.45 * avail:   # never pin more than ~half of the host's free memory
         Ke //= 2                                                        # not enough host memory to pin K = 64 on every rank
         per_call_gb = Be * Ke * 4 * (4 + DIMO + DIMG + 2) / 1e9
         e2e_note = "host memory (%.0f GB available) does not hold K = %d pinned buffers for %d ranks: K reduced" % (avail, args.e2e_fused, local_world)
