@@ -970,6 +970,8 @@ int bpo_env_increase_difficulty(bpo_env* env) {
 
 int bpo_env_get_difficulty(const bpo_env* env) { return env->difficulty; } /* fetch_env.py:96-97 */
 double bpo_env_get_obj_range(const bpo_env* env) { return env->obj_range; }
+/* test hook (mirrors bp_set_ranges): direct write of the curriculum knobs */
+void bpo_env_set_ranges(bpo_env* env, double obj_range, double wrong_obj_range) { env->obj_range = obj_range; env->wrong_obj_range = wrong_obj_range; }
 
 /* _step_callback fetch_env.py:148-167 */
 static void step_callback(bpo_env* env) {

@@ -152,6 +152,7 @@ int bpo_env_set_test(bpo_env* env, float* obs, float* ag, float* g);   /* 0 ok, 
 int bpo_env_increase_difficulty(bpo_env* env);     /* 1 max reached, 0 not, -1 NotImplementedError, -2 AttributeError */
 int bpo_env_get_difficulty(const bpo_env* env);
 double bpo_env_get_obj_range(const bpo_env* env);
+void bpo_env_set_ranges(bpo_env* env, double obj_range, double wrong_obj_range); /* test hook, mirrors bp_set_ranges */
 void bpo_env_get_obs(const bpo_env* env, float* obs, float* ag, float* g);
 void bpo_env_get_state(const bpo_env* env, bpo_env_state* out);
 void bpo_env_set_state(bpo_env* env, const bpo_env_state* in);

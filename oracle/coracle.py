@@ -93,6 +93,7 @@ def lib():
         L.bpo_env_get_difficulty.restype = C.c_int
         L.bpo_env_get_obj_range.argtypes = [vp]
         L.bpo_env_get_obj_range.restype = C.c_double
+        L.bpo_env_set_ranges.argtypes = [vp, C.c_double, C.c_double]
         L.bpo_env_get_state.argtypes = [vp, vp]
         L.bpo_env_set_state.argtypes = [vp, vp]
         L.bpo_env_random_action.argtypes = [vp, vp]
@@ -190,6 +191,10 @@ class OracleVecEnv:
 
     def get_obj_range(self):
         return float(self.L.bpo_env_get_obj_range(self._env_ptr(0)))
+
+    def set_ranges(self, obj_range, wrong_obj_range=0.0):
+        for i in range(self.n):
+            self.L.bpo_env_set_ranges(self._env_ptr(i), float(obj_range), float(wrong_obj_range))
 
     def random_actions(self):
         a = np.zeros((self.n, 4), np.float32)

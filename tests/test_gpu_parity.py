@@ -417,6 +417,25 @@ def test_scripted_push_policy_at_scale_matches_oracle():
         assert torch.equal(out[k], out3[k]), k
 
 
+@pytest.mark.parametrize("name,obj_range", [("GripperTouch-v0", 0.05), ("ToppleTower-v0", 0.06)])
+def test_spawn_rejection_loop_cap(name, obj_range):
+    """the 10 000-attempt cap of the spawn loops.  With obj_range < 0.1 / sqrt(2) the reference's
+    `while norm(xy - gripper) < 0.1` (fetch_env.py:330, 780) can never accept -- it would spin forever; BlockPhys caps
+    the loop.  Kernel and oracle must stop at the same attempt with the same last draw."""
+    env, ref = _make(name, 96, seed=5)
+    env.set_ranges(obj_range); ref.set_ranges(obj_range)
+    o = env.reset(); ro, rag, rg = ref.reset()
+    assert np.array_equal(o["observation"].cpu().numpy(), ro)
+    _assert_state_equal(env, ref, "after a capped spawn")
+    assert (env.get_state()["draws"][:, 0] >= 10000).all()
+    a = torch.zeros(3, 96, 4, device="cuda")
+    out = env.step_fused(a, auto_reset=False)
+    for k in range(3):
+        o2, ag2, r2, s2, _, _ = ref.step(np.zeros((96, 4), np.float32))
+        assert np.array_equal(out["observation"][k].cpu().numpy(), o2)
+    _assert_state_equal(env, ref, "stepping from a capped spawn")
+
+
 def test_gym_single_env_surface():
     """The object the reference gets from gym.make(env_name): reset/step/compute_reward/seed + TimeLimit."""
     import blockpuzzle_gym_b200 as bpg
