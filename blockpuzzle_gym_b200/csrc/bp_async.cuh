@@ -211,16 +211,8 @@ __device__ __forceinline__ uint32_t try_quiet_step(uint32_t* __restrict__ st, co
     g2.q[0] = s_grp[6 * CS + w]; g2.q[1] = s_grp[7 * CS + w]; g2.qv[0] = s_grp[8 * CS + w]; g2.qv[1] = s_grp[9 * CS + w];
     float m[3], ctrl[2];
     action_targets<C::BG>(g2, a, m, ctrl);
-    float lo[3] = {g2.g[0], g2.g[1], g2.g[2]}, hi[3] = {g2.g[0], g2.g[1], g2.g[2]};
-    float qmax = fmaxf(g2.q[0], g2.q[1]);
-#pragma unroll 1
-    for (int sub = 0; sub < kNSub; ++sub) {
-        GripSub gs;
-        substep_gripper<C::BG>(g2, gs, m, ctrl);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) { lo[d] = fminf(lo[d], g2.g[d]); hi[d] = fmaxf(hi[d], g2.g[d]); }
-        if (!C::BG) qmax = fmaxf(qmax, fmaxf(g2.q[0], g2.q[1]));
-    }
+    float lo[3], hi[3], qmax;
+    quiet_gripper_step<C::BG>(g2, m, ctrl, lo, hi, qmax);
     const int nb = (int)((flags >> 9) & 7u);
     bool quiet = true;
 #pragma unroll
@@ -508,174 +500,5 @@ __global__ void __launch_bounds__(32, E == 4 ? 12 : (E == 3 ? 15 : 20)) step_ker
     }
 }
 
-#ifdef BP_EXPERIMENTS
-// ---------------------------------------------------------------------------------------------------
-// step_kernel_duo (BP_STEP_KERNEL=duo; an EXPERIMENT kept for the record, not the default): the same
-// slab and the same env-step functions, served by TWO warps.
-//
-// Idea: the one-warp kernel is latency-bound -- its 22 KB slab limits an SM to 10 resident warps
-// (2.5 per scheduler, ncu: 48 % issue utilisation, half of all stall samples are fixed-latency "wait"),
-// while registers would allow 20 (ptxas: 96 registers, no spills).  Smaller slabs are worse (E = 3: -9 %,
-// E = 2: -30 %: the pending pool gets too small to fill the passes).  So the slab stays and a second
-// warp moves in: warp 0 is the scheduler (picks env-steps, runs the quiet path and finalize), warp 1 the
-// worker (runs the full-physics passes the scheduler hands over, 32 env-steps at a time).  They touch
-// disjoint slab columns, so the only synchronisation is the hand-over, a producer/consumer pair of
-// named barriers:  kBarFull (scheduler arrives, worker waits) and kBarEmpty (worker arrives, scheduler
-// waits only when it needs the worker's batch slot or has too little else to run).  Envs return to the
-// ready pool as soon as the worker clears their pending flag (status words are read volatile).
-// Results stay schedule-independent: each env's steps are still applied in order by the same functions
-// (test_all_step_kernels_agree).
-//
-// Measured on B200 (1 Mi envs, K = 64): 2.41e9 env-steps/s with free-running scheduler (p.tune = 0),
-// 2.76e9 when the scheduler only iterates with all 32 lanes ready -- against 2.84e9 for the one-warp
-// kernel in the same run.  ncu: +40 % executed instructions (the scheduler runs 610 instead of 357
-// iterations per slab because its lanes' own envs sit in the worker's batch), 8.7 instead of 4.9 cycles
-// per issued instruction per warp (instruction-fetch stalls triple with two code paths per slab), and
-// the slab's latency is bounded below by the worker's serial chain of ~48 passes anyway: the hardest env
-// of a slab needs a full-physics pass at almost every one of its 64 steps.  More warps do not shorten
-// that chain; only a shorter pass or more slabs per SM would.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kBarFull = 1, kBarEmpty = 2;
-__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-template <int ID, int E>
-struct Duo {
-    using A = Async<ID, E>;
-    static constexpr int W_CTL = 32;  // uint16 batch[32] (16 words) + ntake + done-epoch (+ padding)
-    static constexpr size_t SMEM = A::SMEM + sizeof(uint32_t) * W_CTL;
-};
-
-template <int ID, int E>
-__global__ void __launch_bounds__(64, 10) step_kernel_duo(uint32_t* __restrict__ st, const __grid_constant__ StepArgs p) {
-    using A = Async<ID, E>;
-    using C = Cfg<ID>;
-    constexpr int NB = C::NB, CS = A::CS;
-    extern __shared__ __align__(16) uint32_t smem[];
-    float* s_cub = reinterpret_cast<float*>(smem);
-    float* s_grp = s_cub + A::W_CUB;
-    uint32_t* s_msc = reinterpret_cast<uint32_t*>(s_grp + A::W_GRP);
-    uint16_t* s_pend = reinterpret_cast<uint16_t*>(s_msc + A::W_MSC);
-    uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_msc + A::W_MSC) + A::W_PEND;
-    uint32_t* s_ctl = s_bits + A::W_BITS;
-    uint16_t* s_batch = reinterpret_cast<uint16_t*>(s_ctl);          // [32] the batch handed to the worker
-    volatile uint32_t* s_ntake = s_ctl + 16;                           // its size (0: worker exits)
-    volatile uint32_t* s_done = s_ctl + 17;                            // batches the worker has completed
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t wbase = (int64_t)blockIdx.x * CS;
-    WarpStats ws;
-
-    const uint32_t f0 = slab_load<ID, E>(st, p, wbase, lane, warp, 2, s_cub, s_grp, s_msc);
-    for (int i = threadIdx.x; i < A::W_BITS; i += 64) s_bits[i] = 0u;
-    if (threadIdx.x == 0) { *s_ntake = 0u; *s_done = 0u; }
-    __syncthreads();
-
-    float n_iter = 0.f, n_pass = 0.f;
-    if (warp == 0) {
-        // ================================================= scheduler
-        int npend = 0;
-        uint32_t submitted = 0;   // batches handed over so far
-        bool inflight = false;    // a batch has been handed over and kBarEmpty not yet consumed
-        while (true) {
-            n_iter += 1.f;
-            int ksel;
-            const int w = pick_ready<E>(s_msc + 2 * CS, lane, p.K, ksel);
-            const bool have = w >= 0;
-            const unsigned any_ready = __ballot_sync(0xffffffffu, have);
-            if (!any_ready && npend == 0) {
-                if (!inflight) break;                      // every env finished its K steps
-                named_bar_sync(kBarEmpty, 64);             // wait for the worker's batch, then look again
-                inflight = false;
-                continue;
-            }
-            // a sparse iteration costs as much as a full one: while the worker still holds a batch and fewer
-            // than p.tune lanes have something to run, wait for its envs to come back instead
-            if (inflight && __popc(any_ready) < p.tune && __shfl_sync(0xffffffffu, *s_done, 0) != submitted) {
-                named_bar_sync(kBarEmpty, 64);
-                inflight = false;
-                continue;
-            }
-            bool want_full = false;
-            if (have) {
-                const uint32_t q = try_quiet_step<ID, E, false>(st, p, wbase + w, w, ksel, s_cub, s_grp, s_msc, s_bits, ws);
-                if (q) {
-                    if (p.auto_reset && ((q >> 2) & 1u)) reset_env_slab<ID, CS, false>(st, p, wbase + w, s_cub + w, s_grp + w, s_msc + w);
-                    s_msc[2 * CS + w] = (uint32_t)(ksel + 1);
-                } else {
-                    want_full = true;
-                }
-            }
-            const unsigned fullm = __ballot_sync(0xffffffffu, want_full);
-            if (want_full) {
-                s_pend[npend + __popc(fullm & ((1u << lane) - 1u))] = (uint16_t)w;
-                s_msc[2 * CS + w] = (uint32_t)ksel | kPendingBit;
-            }
-            npend += __popc(fullm);
-            __syncwarp();
-            // ---- hand a batch to the worker: when 32 are pending, or when nothing else is runnable
-            if (npend >= 32 || (npend > 0 && !any_ready)) {
-                const bool idle = !inflight || (__shfl_sync(0xffffffffu, *s_done, 0) == submitted);
-                // worker still busy and this warp has other work: keep going, hand over later
-                if (!idle && any_ready && npend + 32 <= CS) continue;
-                if (inflight) { named_bar_sync(kBarEmpty, 64); inflight = false; }
-                const int take = npend < 32 ? npend : 32;
-                n_pass += 1.f;
-                if (lane < take) s_batch[lane] = s_pend[lane];
-                if (lane == 0) *s_ntake = (uint32_t)take;
-                const int rest = npend - take;
-                uint16_t mv[E];
-#pragma unroll
-                for (int e = 0; e < E; ++e) mv[e] = (e * 32 + lane < rest) ? s_pend[take + e * 32 + lane] : (uint16_t)0;
-                __syncwarp();
-#pragma unroll
-                for (int e = 0; e < E; ++e)
-                    if (e * 32 + lane < rest) s_pend[e * 32 + lane] = mv[e];
-                npend = rest;
-                __threadfence_block();
-                __syncwarp();
-                named_bar_arrive(kBarFull, 64);
-                inflight = true;
-                submitted += 1;
-            }
-        }
-        if (lane == 0) *s_ntake = 0u;   // tell the worker to exit
-        __threadfence_block();
-        __syncwarp();
-        named_bar_arrive(kBarFull, 64);
-    } else {
-        // ================================================= worker
-        uint32_t epoch = 0;
-        while (true) {
-            named_bar_sync(kBarFull, 64);
-            const int take = (int)*s_ntake;
-            if (take == 0) break;
-            int pw = 0, k = 0;
-            if (lane < take) {
-                pw = s_batch[lane];
-                k = (int)(s_msc[2 * CS + pw] & 0xffffu);
-                const uint32_t code = full_step_item<ID, E, false>(st, p, wbase + pw, pw, k, s_cub, s_grp, s_msc, s_bits, ws);
-                if (p.auto_reset && (code & 2u)) reset_env_slab<ID, CS, false>(st, p, wbase + pw, s_cub + pw, s_grp + pw, s_msc + pw);
-            }
-            __threadfence_block();                        // the env's state before its status word
-            if (lane < take) *reinterpret_cast<volatile uint32_t*>(s_msc + 2 * CS + pw) = (uint32_t)(k + 1);  // clears the pending flag
-            __syncwarp();
-            epoch += 1;
-            if (lane == 0) *s_done = epoch;
-            __threadfence_block();
-            __syncwarp();
-            named_bar_arrive(kBarEmpty, 64);
-        }
-    }
-    __syncthreads();
-    slab_flush<ID, E, false>(st, p, wbase, lane, warp, 2, s_cub, s_grp, s_msc, s_bits, f0);
-    add_warp_stats(p, ws, lane);
-    if (warp == 0 && lane == 0 && p.stats) {
-        atomicAdd(p.stats + 6, (double)n_iter);
-        atomicAdd(p.stats + 7, (double)n_pass);
-    }
-}
-
-#endif  // BP_EXPERIMENTS
 
 }  // namespace bp

@@ -17,6 +17,8 @@
 #pragma once
 #include <cstdint>
 
+#include "bp_tables.cuh"
+
 namespace bp {
 
 // ---------------------------------------------------------------- constants
@@ -168,9 +170,6 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return x 
 // BlockPhys v1.1: the fused multiply-adds of the spec are written explicitly (the file is compiled
 // with -fmad=false, so nothing else is ever contracted)
 #define F(a, b, c) __fmaf_rn((a), (b), (c))
-#ifndef BP_PACKED_F32X2
-#define BP_PACKED_F32X2 1   // packed f32x2 arithmetic (sm_100+) in the gripper / finger integrators
-#endif
 
 // ---------------------------------------------------------------- env state in registers
 template <int NB>
@@ -215,6 +214,12 @@ __device__ __forceinline__ void sim_init(Env<NB>& e, bool tower) {
 struct Blk { float x, y, z, c, s, vx, vy, vz, w; };
 struct Grip { float g[3], gv[3], q[2], qv[2]; };
 struct GripSub { float gox, goy, qo[2], closed[2]; };
+// BlockPhys v2: the env-step's propagator base.  The weld and the finger actuators are linear, so until a contact acts
+// on a channel its state after n substeps is the n-th power of the substep map (bp_tables.cuh) applied to the state the
+// env-step started from (d0 / e0 = position - target, v0 / w0 = velocity).  x and y are never acted on; z leaves the
+// propagator when a finger lands on a cube (det bit 0), a finger when its closing is undone (bits 1 / 2) -- from then
+// on that channel advances by the substep recurrence.
+struct GripStep { float d0[3], v0[3], e0[2], w0[2]; uint32_t det; };
 
 template <int NB, int STRIDE, int SSTRIDE = STRIDE>
 struct Col {
@@ -325,7 +330,7 @@ __device__ __forceinline__ bool over_table(float x, float y) {
 // finger f (0: +y, 1: -y) against cube b (index bi); ox/oy: the cube's start-of-substep position
 // Returns false when the pair is not penetrating (nothing but `contacts` was touched), true when the response ran
 // and the cube, the gripper height or the finger opening may have changed.
-__device__ __forceinline__ bool collide_finger_block(Grip& e, GripSub& st, const int f, Blk& b, const float ox, const float oy,
+__device__ __forceinline__ bool collide_finger_block(Grip& e, GripSub& st, GripStep& sb, const int n, const int f, Blk& b, const float ox, const float oy,
                                                      float& dth_acc, bool& rotated, uint32_t& sup, uint32_t& contacts, const int bi) {
     const float sgn = f == 0 ? 1.0f : -1.0f;
     const float qf = f == 0 ? e.q[0] : e.q[1];
@@ -348,6 +353,10 @@ __device__ __forceinline__ bool collide_finger_block(Grip& e, GripSub& st, const
             sup |= 1u << bi;
         } else {
             e.g[2] = (b.z + (kFZ + kHB)) - kFZOff;
+            if (!(sb.det & 1u)) {   // z leaves the propagator with the velocity it has there at this substep
+                e.gv[2] = F(kGC[n], sb.d0[2], kGD[n] * sb.v0[2]);
+                sb.det |= 1u;
+            }
             if (e.gv[2] < 0.0f) e.gv[2] = 0.0f;
         }
         return true;
@@ -365,6 +374,7 @@ __device__ __forceinline__ bool collide_finger_block(Grip& e, GripSub& st, const
                 q_now = qf + yield;
                 if (f == 0) { e.q[0] = q_now; e.qv[0] = 0.0f; st.closed[0] = closed - yield; }
                 else { e.q[1] = q_now; e.qv[1] = 0.0f; st.closed[1] = closed - yield; }
+                sb.det |= 2u << f;   // this finger advances by the recurrence for the rest of the env-step
                 delta = delta - yield;
             }
             if (!(delta > 0.0f)) return true;
@@ -448,66 +458,123 @@ __device__ __forceinline__ bool collide_block_block(Blk& a, const float aox, con
     return true;
 }
 
-// the gripper part of one substep (steps 1-2 of the spec)
+// the gripper part of substep n (1..20) of an env-step (steps 1-2 of the spec, BlockPhys v2)
 template <bool BG>
-__device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const float m[3], const float ctrl[2]) {
+__device__ __forceinline__ void grip_step_begin(const Grip& e, const float m[3], const float ctrl[2], GripStep& sb) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { sb.d0[d] = e.g[d] - m[d]; sb.v0[d] = e.gv[d]; }
+#pragma unroll
+    for (int f = 0; f < 2; ++f) { sb.e0[f] = BG ? 0.0f : e.q[f] - ctrl[f]; sb.w0[f] = BG ? 0.0f : e.qv[f]; }
+    sb.det = 0;
+}
+
+template <bool BG>
+__device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const float m[3], const float ctrl[2], const GripStep& sb, const int n) {
     st.closed[0] = st.closed[1] = 0.0f;
     st.gox = e.g[0]; st.goy = e.g[1];
     st.qo[0] = e.q[0]; st.qo[1] = e.q[1];
-#if BP_PACKED_F32X2
-    {   // x and y as one packed pair: Blackwell's f32x2 instructions are two independent IEEE operations, so the
-        // results are bit-identical to the scalar form (m - g is written as m + (-g): the same rounded value)
-        const float2 d = __fadd2_rn(make_float2(m[0], m[1]), make_float2(-e.g[0], -e.g[1]));
-        const float2 t = __fmul2_rn(make_float2(-kBW, -kBW), make_float2(e.gv[0], e.gv[1]));   // (-b) * v == -(b * v)
-        const float2 acc = __ffma2_rn(make_float2(kKW, kKW), d, t);
-        const float2 gv = __ffma2_rn(acc, make_float2(kH, kH), make_float2(e.gv[0], e.gv[1]));
-        const float2 g = __ffma2_rn(gv, make_float2(kH, kH), make_float2(e.g[0], e.g[1]));
-        e.gv[0] = gv.x; e.gv[1] = gv.y; e.g[0] = g.x; e.g[1] = g.y;
+    const float ga = kGA[n], gb = kGB[n];
+    e.g[0] = F(ga, sb.d0[0], F(gb, sb.v0[0], m[0]));
+    e.g[1] = F(ga, sb.d0[1], F(gb, sb.v0[1], m[1]));
+    if (!(sb.det & 1u)) {   // free: the propagator, projected onto z >= kGZMin (finger bottoms on the table)
+        const float zv = F(ga, sb.d0[2], F(gb, sb.v0[2], m[2]));
+        e.g[2] = zv < kGZMin ? kGZMin : zv;
+    } else {
         const float az = F(kKW, m[2] - e.g[2], -(kBW * e.gv[2]));
         e.gv[2] = F(az, kH, e.gv[2]);
         e.g[2] = F(e.gv[2], kH, e.g[2]);
-    }
-#else
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float acc = F(kKW, m[k] - e.g[k], -(kBW * e.gv[k]));
-        e.gv[k] = F(acc, kH, e.gv[k]);
-        e.g[k] = F(e.gv[k], kH, e.g[k]);
-    }
-#endif
-    // the limits below are written as selects (no divergent branches in the 20-substep loop)
-    {
         const bool low = e.g[2] < kGZMin;
         e.gv[2] = (low && e.gv[2] < 0.0f) ? 0.0f : e.gv[2];
         e.g[2] = low ? kGZMin : e.g[2];
     }
     if (!BG) {
-#if BP_PACKED_F32X2
-        const float2 fd = __fadd2_rn(make_float2(ctrl[0], ctrl[1]), make_float2(-e.q[0], -e.q[1]));
-        const float2 ft = __fmul2_rn(make_float2(-kBF, -kBF), make_float2(e.qv[0], e.qv[1]));
-        const float2 facc = __ffma2_rn(make_float2(kKF, kKF), fd, ft);
-        const float2 fqv = __ffma2_rn(facc, make_float2(kH, kH), make_float2(e.qv[0], e.qv[1]));
-        const float2 fq = __ffma2_rn(fqv, make_float2(kH, kH), make_float2(e.q[0], e.q[1]));
-#endif
+        const float fa = kFA[n], fb = kFB[n];
 #pragma unroll
         for (int f = 0; f < 2; ++f) {
             const float q_old = e.q[f];
-#if BP_PACKED_F32X2
-            float qv = f == 0 ? fqv.x : fqv.y;
-            float q = f == 0 ? fq.x : fq.y;
-#else
-            const float acc = F(kKF, ctrl[f] - e.q[f], -(kBF * e.qv[f]));
-            float qv = F(acc, kH, e.qv[f]);
-            float q = F(qv, kH, e.q[f]);
-#endif
-            const bool low = q < 0.0f;
-            qv = (low && qv < 0.0f) ? 0.0f : qv;
-            q = low ? 0.0f : q;
-            const bool high = q > kQMax;
-            qv = (high && qv > 0.0f) ? 0.0f : qv;
-            q = high ? kQMax : q;
-            e.q[f] = q; e.qv[f] = qv;
+            float q;
+            if (!(sb.det & (2u << f))) {   // free: the propagator, projected onto the joint range
+                q = clampf(F(fa, sb.e0[f], F(fb, sb.w0[f], ctrl[f])), 0.0f, kQMax);
+            } else {
+                const float acc = F(kKF, ctrl[f] - e.q[f], -(kBF * e.qv[f]));
+                float qv = F(acc, kH, e.qv[f]);
+                q = F(qv, kH, e.q[f]);
+                const bool low = q < 0.0f;
+                qv = (low && qv < 0.0f) ? 0.0f : qv;
+                q = low ? 0.0f : q;
+                const bool high = q > kQMax;
+                qv = (high && qv > 0.0f) ? 0.0f : qv;
+                q = high ? kQMax : q;
+                e.qv[f] = qv;
+            }
+            e.q[f] = q;
             st.closed[f] = fmaxf(q_old - q, 0.0f);
+        }
+    }
+}
+
+// end of the env-step: the velocities of the channels that stayed free, with the limit rules applied once
+template <bool BG>
+__device__ __forceinline__ void grip_step_end(Grip& e, const float m[3], const float ctrl[2], const GripStep& sb) {
+    e.gv[0] = F(kGC20, sb.d0[0], kGD20 * sb.v0[0]);
+    e.gv[1] = F(kGC20, sb.d0[1], kGD20 * sb.v0[1]);
+    if (!(sb.det & 1u)) {
+        const float zv = F(kGA20, sb.d0[2], F(kGB20, sb.v0[2], m[2]));
+        const float v = F(kGC20, sb.d0[2], kGD20 * sb.v0[2]);
+        e.gv[2] = (zv < kGZMin && v < 0.0f) ? 0.0f : v;
+    }
+    if (!BG) {
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            if (!(sb.det & (2u << f))) {
+                const float qf = F(kFA20, sb.e0[f], F(kFB20, sb.w0[f], ctrl[f]));
+                float v = F(kFC20, sb.e0[f], kFD20 * sb.w0[f]);
+                v = (qf < 0.0f && v < 0.0f) ? 0.0f : v;
+                v = (qf > kQMax && v > 0.0f) ? 0.0f : v;
+                e.qv[f] = v;
+            }
+        }
+    }
+}
+
+// The whole env-step of the gripper when nothing acts on it: the propagator's 20th power (bit for bit what
+// substep_gripper x 20 + grip_step_end leave when no contact event occurs), plus a box [lo, hi] and a finger opening
+// bound qmax that contain the gripper at EVERY substep n = 1..20: the state at substep n is GA[n] d0 + GB[n] v0 past
+// the target with GA[n] in [kGAMin, kGAMax] and GB[n] in [kGBMin, kGBMax] (all positive), so the interval product
+// bounds it; likewise the fingers.  (The bound is not part of the model: it only decides which path computes the step.)
+template <bool BG>
+__device__ __forceinline__ void quiet_gripper_step(Grip& e, const float m[3], const float ctrl[2], float lo[3], float hi[3], float& qmax) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float d0 = e.g[d] - m[d], v0 = e.gv[d];
+        const float a1 = kGAMin * d0, a2 = kGAMax * d0, b1 = kGBMin * v0, b2 = kGBMax * v0;
+        lo[d] = m[d] + (fminf(a1, a2) + fminf(b1, b2));
+        hi[d] = m[d] + (fmaxf(a1, a2) + fmaxf(b1, b2));
+        const float gn = F(kGA20, d0, F(kGB20, v0, m[d]));
+        const float vn = F(kGC20, d0, kGD20 * v0);
+        if (d < 2) {
+            e.g[d] = gn; e.gv[d] = vn;
+        } else {
+            const bool low = gn < kGZMin;
+            e.g[2] = low ? kGZMin : gn;
+            e.gv[2] = (low && vn < 0.0f) ? 0.0f : vn;
+            lo[2] = fmaxf(lo[2], kGZMin); hi[2] = fmaxf(hi[2], kGZMin);
+        }
+    }
+    qmax = fmaxf(e.q[0], e.q[1]);
+    if (!BG) {
+        qmax = 0.0f;
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            const float e0 = e.q[f] - ctrl[f], w0 = e.qv[f];
+            const float top = ctrl[f] + (fmaxf(kFAMin * e0, kFAMax * e0) + fmaxf(kFBMin * w0, kFBMax * w0));
+            qmax = fmaxf(qmax, clampf(top, 0.0f, kQMax));
+            const float qf = F(kFA20, e0, F(kFB20, w0, ctrl[f]));
+            float v = F(kFC20, e0, kFD20 * w0);
+            v = (qf < 0.0f && v < 0.0f) ? 0.0f : v;
+            v = (qf > kQMax && v > 0.0f) ? 0.0f : v;
+            e.q[f] = clampf(qf, 0.0f, kQMax);
+            e.qv[f] = v;
         }
     }
 }
@@ -515,7 +582,7 @@ __device__ __forceinline__ void substep_gripper(Grip& e, GripSub& st, const floa
 // the cube part of one substep (steps 3-5 of the spec).  Returns true when the substep left every
 // cube bit-for-bit unchanged (all at rest before and after, nothing moved or rotated): a fixed point.
 template <int NB, int STRIDE, int SS>
-__device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB, STRIDE, SS> col, const int nb, uint32_t& contacts) {
+__device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, GripStep& sb, const int n, const Col<NB, STRIDE, SS> col, const int nb, uint32_t& contacts) {
     uint32_t sup = 0;
     bool rest = true, rotated = false;
     contacts = 0;
@@ -554,7 +621,7 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, const Col<NB
         const float ox = col.scr(i, 0), oy = col.scr(i, 1);
         float dth = col.scr(i, 3);
 #pragma unroll 1
-        for (int f = 0; f < 2; ++f) collide_finger_block(e, st, f, b, ox, oy, dth, rotated, sup, contacts, i);
+        for (int f = 0; f < 2; ++f) collide_finger_block(e, st, sb, n, f, b, ox, oy, dth, rotated, sup, contacts, i);
         col.scr(i, 3) = dth;
         col.store_pose(i, b);
     }
@@ -623,13 +690,16 @@ template <int NB, int STRIDE, bool BG, int SS>
 __device__ __forceinline__ bool sim_step_col(Grip& g, const float a[4], const Col<NB, STRIDE, SS> col, const int nb, uint32_t& contacts) {
     float m[3], ctrl[2];
     action_targets<BG>(g, a, m, ctrl);
+    GripStep sb;
+    grip_step_begin<BG>(g, m, ctrl, sb);
     bool still = false;
 #pragma unroll 1
-    for (int sub = 0; sub < kNSub; ++sub) {
+    for (int n = 1; n <= kNSub; ++n) {
         GripSub st;
-        substep_gripper<BG>(g, st, m, ctrl);
-        still = substep_cubes<NB, STRIDE, SS>(g, st, col, nb, contacts);
+        substep_gripper<BG>(g, st, m, ctrl, sb, n);
+        still = substep_cubes<NB, STRIDE, SS>(g, st, sb, n, col, nb, contacts);
     }
+    grip_step_end<BG>(g, m, ctrl, sb);
     return still;
 }
 
@@ -716,7 +786,7 @@ __device__ __forceinline__ uint32_t pair_candidates(const CubeRegs<NB>& q, const
 }
 
 template <int NB, bool VAR>
-__device__ __forceinline__ bool substep_cubes_reg(Grip& e, GripSub& st, CubeRegs<NB>& q, const int nb, uint32_t& contacts) {
+__device__ __forceinline__ bool substep_cubes_reg(Grip& e, GripSub& st, GripStep& sb, const int n, CubeRegs<NB>& q, const int nb, uint32_t& contacts) {
     uint32_t sup = 0;
     bool rest = true, rotated = false;
     contacts = 0;
@@ -754,7 +824,7 @@ __device__ __forceinline__ bool substep_cubes_reg(Grip& e, GripSub& st, CubeRegs
         const int i = slot >> 1, f = slot & 1;
         Blk b{pick<NB>(q.x, i), pick<NB>(q.y, i), pick<NB>(q.z, i), pick<NB>(q.c, i), pick<NB>(q.s, i), 0.0f, 0.0f, 0.0f, 0.0f};
         float dth = pick<NB>(q.dth, i);
-        if (collide_finger_block(e, st, f, b, pick<NB>(q.ox, i), pick<NB>(q.oy, i), dth, rotated, sup, contacts, i)) {
+        if (collide_finger_block(e, st, sb, n, f, b, pick<NB>(q.ox, i), pick<NB>(q.oy, i), dth, rotated, sup, contacts, i)) {
             put<NB>(q.x, i, b.x); put<NB>(q.y, i, b.y); put<NB>(q.z, i, b.z); put<NB>(q.c, i, b.c); put<NB>(q.s, i, b.s);
             put<NB>(q.dth, i, dth);
             fm = finger_candidates<NB, VAR>(e, q, nb) & ~((2u << slot) - 1u);
@@ -825,13 +895,16 @@ template <int NB, bool BG, bool VAR>
 __device__ __forceinline__ bool sim_step_reg(Grip& g, const float a[4], CubeRegs<NB>& q, const int nb, uint32_t& contacts) {
     float m[3], ctrl[2];
     action_targets<BG>(g, a, m, ctrl);
+    GripStep sb;
+    grip_step_begin<BG>(g, m, ctrl, sb);
     bool still = false;
 #pragma unroll 1
-    for (int sub = 0; sub < kNSub; ++sub) {
+    for (int n = 1; n <= kNSub; ++n) {
         GripSub st;
-        substep_gripper<BG>(g, st, m, ctrl);
-        still = substep_cubes_reg<NB, VAR>(g, st, q, nb, contacts);
+        substep_gripper<BG>(g, st, m, ctrl, sb, n);
+        still = substep_cubes_reg<NB, VAR>(g, st, sb, n, q, nb, contacts);
     }
+    grip_step_end<BG>(g, m, ctrl, sb);
     return still;
 }
 

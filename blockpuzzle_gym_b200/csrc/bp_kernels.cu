@@ -265,352 +265,6 @@ __global__ void __launch_bounds__(128) step_kernel_simple(uint32_t* st, StepArgs
     }
 }
 
-#ifdef BP_EXPERIMENTS   // lab notebook: the CTA-tiled kernel of the first design (make EXPERIMENTS=1)
-// ---------------------------------------------------------------- tiled step kernel
-// One CTA of 128 threads owns a tile of 256 envs for all K fused steps.  Cube state lives in shared
-// memory (SoA), the gripper state of each env in the registers of its owner thread (2 envs/thread).
-// Every step has three phases:
-//   A  owners: clip the action, integrate the gripper alone (20 substeps) while tracking the swept
-//      finger volume.  If the cubes sit on an exact fixed point and the swept volume cannot reach
-//      any cube, the step is "quiet": its result is the gripper trajectory just computed and the
-//      stored cube-contact set.  Otherwise the env id goes to the tile's active list.
-//   B  workers: the active list is compacted, so full 32-lane warps run the complete BlockPhys step
-//      (gripper + cubes + contacts) for exactly the envs that need it.
-//   C  owners: touch matrix / reward / latch / TimeLimit, observation rows staged through shared
-//      memory and written with fully coalesced stores, auto-reset.
-// The quiet path is result-neutral (see cube_out_of_reach), so outputs are bit-identical to the
-// simple kernel and to the oracle.
-template <int ID>
-struct Tile {
-    using C = Cfg<ID>;
-    static constexpr int NB = C::NB;
-    static constexpr int TILE = 256, THREADS = 128, EPT = 2, NW = THREADS / 32;
-    // rows that are 16-byte multiples are staged unpadded and moved with 128-bit accesses; others
-    // get an odd row stride (conflict-free scalar STS)
-    static constexpr int OSTR = (C::DIMO % 4 == 0) ? C::DIMO : ((C::DIMO % 2 == 0) ? C::DIMO + 1 : C::DIMO);
-    static constexpr int GSTR = (C::DIMG % 4 == 0) ? C::DIMG : ((C::DIMG % 2 == 0) ? C::DIMG + 1 : C::DIMG);
-    static constexpr int STAGE = 32 * OSTR;
-    static constexpr int W_COL = Col<NB, THREADS>::kFields * THREADS;  // private worker columns, aliased with the stage
-    static constexpr int W_STAGE = (NW * STAGE > W_COL) ? NW * STAGE : W_COL;
-    static constexpr int W_BLK = 9 * NB * TILE, W_GRIP = 10 * TILE, W_ACT = 4 * TILE, W_CTC = TILE, W_LIST = TILE / 2;
-    static constexpr size_t SMEM = sizeof(uint32_t) * (size_t)(W_BLK + W_GRIP + W_ACT + W_CTC + W_STAGE + W_LIST + 4);
-};
-
-// flush `nv` staged rows (row stride SSTR in shared memory) of W floats each to a contiguous global range
-template <int W, int SSTR>
-__device__ __forceinline__ void flush_rows(const float* stage, float* __restrict__ dst, int nv, int lane) {
-    if constexpr (W % 4 == 0) {
-        // rows are 16-byte multiples: the stage is a linear image of the global range -> 128-bit copies
-        static_assert(SSTR == W, "vector path needs unpadded rows");
-        const int total4 = nv * (W / 4);
-        const float4* s4 = reinterpret_cast<const float4*>(stage);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = lane; i < total4; i += 32) d4[i] = s4[i];
-    } else {
-        const int total = nv * W;
-        for (int idx = lane; idx < total; idx += 32) {
-            const int row = idx / W, col = idx - row * W;
-            dst[idx] = stage[row * SSTR + col];
-        }
-    }
-}
-
-// write one row of W floats produced by `gen(put)` into the warp's stage at row `lane`
-template <int W, int SSTR, class Gen>
-__device__ __forceinline__ void stage_row(float* stage, int lane, Gen&& gen) {
-    if constexpr (W % 4 == 0) {
-        float row[W];
-        gen([&](int c, float v) { row[c] = v; });
-        float4* s4 = reinterpret_cast<float4*>(stage) + lane * (W / 4);
-#pragma unroll
-        for (int j = 0; j < W / 4; ++j) s4[j] = make_float4(row[4 * j], row[4 * j + 1], row[4 * j + 2], row[4 * j + 3]);
-    } else {
-        float* srow = stage + lane * SSTR;
-        gen([&](int c, float v) { srow[c] = v; });
-    }
-}
-
-// RobotEnv.reset for one env of a tile: kept out of line (it is rare and large: Philox, log, sincos)
-template <int ID>
-__device__ __noinline__ void reset_in_tile(uint32_t* __restrict__ st, const StepArgs& p, int64_t gi, int64_t li, Grip& gr,
-                                           float* blk_col /* s_blk + le, stride TILE */, int& nb, uint32_t& touch_now, uint32_t& touch_ever, uint32_t& priv) {
-    using C = Cfg<ID>;
-    constexpr int NB = C::NB;
-    constexpr int NF = num_fields<NB>();
-    constexpr int TILE = 256;
-    Env<NB> e;
-    e.nb = nb;
-    e.touch_now = touch_now; e.touch_ever = touch_ever;
-    e.episode = st[(int64_t)(NF - 5) * p.stateB + gi];
-    e.key0 = st[(int64_t)(NF - 2) * p.stateB + gi]; e.key1 = st[(int64_t)(NF - 1) * p.stateB + gi];
-    env_reset<ID>(e, p.rg);
-    st[(int64_t)(NF - 5) * p.stateB + gi] = e.episode;
-    st[(int64_t)(NF - 4) * p.stateB + gi] = e.draws0;
-    st[(int64_t)(NF - 3) * p.stateB + gi] = e.draws1;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) { gr.g[d] = e.g[d]; gr.gv[d] = e.gv[d]; }
-    gr.q[0] = e.q[0]; gr.q[1] = e.q[1]; gr.qv[0] = e.qv[0]; gr.qv[1] = e.qv[1];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        float* bb = blk_col + (9 * b) * TILE;
-        bb[0] = e.px[b]; bb[TILE] = e.py[b]; bb[2 * TILE] = e.pz[b]; bb[3 * TILE] = e.c[b]; bb[4 * TILE] = e.s[b];
-        bb[5 * TILE] = e.vx[b]; bb[6 * TILE] = e.vy[b]; bb[7 * TILE] = e.vz[b]; bb[8 * TILE] = e.w[b];
-    }
-    nb = e.nb; touch_now = e.touch_now; touch_ever = e.touch_ever; priv = e.priv;
-    if (p.reset_obs) write_row_obs<ID>(e, p.reset_obs + li * C::DIMO);
-    if (p.reset_ag) write_row_ag<ID>(e, p.reset_ag + li * C::DIMG);
-}
-
-template <int ID>
-__global__ void __launch_bounds__(128, 4) step_kernel_tiled(uint32_t* __restrict__ st, const __grid_constant__ StepArgs p) {
-    using T = Tile<ID>;
-    using C = Cfg<ID>;
-    constexpr int NB = C::NB, TILE = T::TILE, EPT = T::EPT, NW = T::NW;
-    constexpr int NF = num_fields<NB>();
-    extern __shared__ __align__(16) uint32_t smem[];
-    float* s_blk = reinterpret_cast<float*>(smem);                  // [9*NB][TILE]
-    float* s_grip = s_blk + T::W_BLK;                               // [10][TILE]  gripper state exchange for active envs
-    float* s_act = s_grip + T::W_GRIP;                              // [4][TILE]   clipped action of active envs
-    uint32_t* s_ctc = reinterpret_cast<uint32_t*>(s_act + T::W_ACT);  // [TILE] in: nb; out: contacts | static << 31
-    float* s_stage = reinterpret_cast<float*>(s_ctc + T::W_CTC);    // [NW][STAGE]
-    uint16_t* s_list = reinterpret_cast<uint16_t*>(s_stage + T::W_STAGE);  // [TILE]
-    int* s_nact = reinterpret_cast<int*>(s_list + TILE);            // [2] double-buffered active counter
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t tile0 = (int64_t)blockIdx.x * TILE;  // launch-local index of the tile's env 0
-    float* my_stage = s_stage + warp * T::STAGE;
-    const Col<NB, T::THREADS> wcol(s_stage + tid);  // worker column (phase B only; the stage is idle then)
-
-    // ---- owner state, 2 envs per thread: slot j owns local env le = j*128 + tid
-    Grip gr[EPT];
-    uint32_t touch_now[EPT], touch_ever[EPT], priv[EPT];
-    int tt[EPT], succ[EPT], nb[EPT];
-    bool live[EPT];
-    float n_ep = 0.f, n_su = 0.f, n_st = 0.f, n_inv = 0.f, r_sum = 0.f, n_act = 0.f;
-
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        const int le = j * T::THREADS + tid;
-        const int64_t li = tile0 + le;
-        live[j] = li < p.B;
-        const int64_t gi = p.env0 + (live[j] ? li : 0);
-        const uint32_t* q = st + gi;
-        int f = 0;
-        auto ldf = [&]() { float v = __uint_as_float(q[(int64_t)f * p.stateB]); ++f; return v; };
-        auto ldu = [&]() { uint32_t v = q[(int64_t)f * p.stateB]; ++f; return v; };
-        gr[j].g[0] = ldf(); gr[j].g[1] = ldf(); gr[j].g[2] = ldf();
-        gr[j].gv[0] = ldf(); gr[j].gv[1] = ldf(); gr[j].gv[2] = ldf();
-        gr[j].q[0] = ldf(); gr[j].q[1] = ldf(); gr[j].qv[0] = ldf(); gr[j].qv[1] = ldf();
-#pragma unroll
-        for (int w = 0; w < 9 * NB; ++w) s_blk[w * TILE + le] = ldf();
-        const uint32_t touch = ldu();
-        touch_now[j] = touch & 0xffffu; touch_ever[j] = touch >> 16;
-        const uint32_t flags = ldu();
-        tt[j] = (int)(flags & 0xffu); succ[j] = (int)((flags >> 8) & 1u); nb[j] = (int)((flags >> 9) & 7u);
-        priv[j] = ldu();
-    }
-    if (tid < 2) s_nact[tid] = 0;
-    __syncthreads();
-
-    for (int k = 0; k < p.K; ++k) {
-        float act[EPT][4];
-        uint32_t ctc[EPT];
-        bool active[EPT];
-        int inv = 0;
-        int* nact = s_nact + (k & 1);
-        // ------------------------------------------------------------ phase A
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            const int le = j * T::THREADS + tid;
-            const int64_t li = tile0 + le;
-            active[j] = false;
-            ctc[j] = 0;
-            if (!live[j]) continue;
-            const int64_t row = (int64_t)k * p.B + li;
-            float4 a4;
-            if (p.actions) {
-                a4 = __ldg(reinterpret_cast<const float4*>(p.actions) + row);
-            } else {
-                const int64_t gi = p.env0 + li;
-                const uint32_t ep = st[(int64_t)(NF - 5) * p.stateB + gi];
-                const uint32_t k0 = st[(int64_t)(NF - 2) * p.stateB + gi], k1 = st[(int64_t)(NF - 1) * p.stateB + gi];
-                U4 w = philox4x32((uint32_t)tt[j], ep - 1u, 2u, 0u, k0, k1);
-                a4 = make_float4(2.0f * u01(w.x) - 1.0f, 2.0f * u01(w.y) - 1.0f, 2.0f * u01(w.z) - 1.0f, 2.0f * u01(w.w) - 1.0f);
-            }
-            if (p.actions_out) reinterpret_cast<float4*>(p.actions_out)[row] = a4;
-            act[j][0] = a4.x; act[j][1] = a4.y; act[j][2] = a4.z; act[j][3] = a4.w;
-            clip_action(act[j], inv);
-            bool quiet = (priv[j] >> 31) != 0;
-            Grip g2 = gr[j];
-            if (quiet) {
-                float m[3], ctrl[2];
-                action_targets<C::BG>(g2, act[j], m, ctrl);
-                float lo[3] = {g2.g[0], g2.g[1], g2.g[2]}, hi[3] = {g2.g[0], g2.g[1], g2.g[2]};
-                float qmax = fmaxf(g2.q[0], g2.q[1]);
-#pragma unroll 4
-                for (int sub = 0; sub < kNSub; ++sub) {
-                    GripSub gs;
-                    substep_gripper<C::BG>(g2, gs, m, ctrl);
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) { lo[d] = fminf(lo[d], g2.g[d]); hi[d] = fmaxf(hi[d], g2.g[d]); }
-                    if (!C::BG) qmax = fmaxf(qmax, fmaxf(g2.q[0], g2.q[1]));
-                }
-#pragma unroll
-                for (int b = 0; b < NB; ++b) {
-                    if (b < nb[j]) {
-                        const float* bb = s_blk + (9 * b) * TILE + le;
-                        quiet = quiet && cube_out_of_reach(bb[0], bb[TILE], bb[2 * TILE], bb[3 * TILE], bb[4 * TILE], lo, hi, qmax);
-                    }
-                }
-            }
-            if (quiet) {
-                gr[j] = g2;
-                ctc[j] = priv[j] & 0x7fffu;
-                if (over_table(g2.g[0], g2.g[1]) && g2.g[2] - kGZMin < kMargin) ctc[j] |= pair_bit(0, 1);
-            } else {
-                active[j] = true;
-                n_act += 1.f;
-#pragma unroll
-                for (int d = 0; d < 3; ++d) { s_grip[d * TILE + le] = gr[j].g[d]; s_grip[(3 + d) * TILE + le] = gr[j].gv[d]; }
-                s_grip[6 * TILE + le] = gr[j].q[0]; s_grip[7 * TILE + le] = gr[j].q[1];
-                s_grip[8 * TILE + le] = gr[j].qv[0]; s_grip[9 * TILE + le] = gr[j].qv[1];
-#pragma unroll
-                for (int d = 0; d < 4; ++d) s_act[d * TILE + le] = act[j][d];
-                s_ctc[le] = (uint32_t)nb[j];
-                const int slot = atomicAdd(nact, 1);
-                s_list[slot] = (uint16_t)le;
-            }
-        }
-        __syncthreads();
-        // ------------------------------------------------------------ phase B
-        {
-            const int n = *nact;
-            for (int base = warp * 32; base < n; base += NW * 32) {
-                const int i = base + lane;
-                if (i < n) {
-                    const int le = s_list[i];
-                    Grip g;
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) { g.g[d] = s_grip[d * TILE + le]; g.gv[d] = s_grip[(3 + d) * TILE + le]; }
-                    g.q[0] = s_grip[6 * TILE + le]; g.q[1] = s_grip[7 * TILE + le];
-                    g.qv[0] = s_grip[8 * TILE + le]; g.qv[1] = s_grip[9 * TILE + le];
-#pragma unroll
-                    for (int w = 0; w < 9 * NB; ++w) wcol.p[w * T::THREADS] = s_blk[w * TILE + le];
-                    const int nbv = (int)s_ctc[le];
-                    float a[4] = {s_act[le], s_act[TILE + le], s_act[2 * TILE + le], s_act[3 * TILE + le]};
-                    uint32_t contacts = 0;
-                    const bool is_static = sim_step_col<NB, T::THREADS, C::BG>(g, a, wcol, nbv, contacts);
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) { s_grip[d * TILE + le] = g.g[d]; s_grip[(3 + d) * TILE + le] = g.gv[d]; }
-                    s_grip[6 * TILE + le] = g.q[0]; s_grip[7 * TILE + le] = g.q[1];
-                    s_grip[8 * TILE + le] = g.qv[0]; s_grip[9 * TILE + le] = g.qv[1];
-#pragma unroll
-                    for (int w = 0; w < 9 * NB; ++w) s_blk[w * TILE + le] = wcol.p[w * T::THREADS];
-                    s_ctc[le] = contacts | (is_static ? 0x80000000u : 0u);
-                }
-            }
-            if (tid == 0) s_nact[(k + 1) & 1] = 0;
-        }
-        __syncthreads();
-        // ------------------------------------------------------------ phase C
-#pragma unroll
-        for (int j = 0; j < EPT; ++j) {
-            const int le = j * T::THREADS + tid;
-            const int64_t li = tile0 + le;
-            const int64_t rg0 = tile0 + j * T::THREADS + warp * 32;  // launch-local index of this row group's env 0
-            int nv = (int)((p.B - rg0) < 32 ? (p.B - rg0) : 32);
-            if (nv < 0) nv = 0;
-            const int64_t row = (int64_t)k * p.B + li;
-            bool fail = false, done = false;
-            if (live[j]) {
-                if (active[j]) {
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) { gr[j].g[d] = s_grip[d * TILE + le]; gr[j].gv[d] = s_grip[(3 + d) * TILE + le]; }
-                    gr[j].q[0] = s_grip[6 * TILE + le]; gr[j].q[1] = s_grip[7 * TILE + le];
-                    gr[j].qv[0] = s_grip[8 * TILE + le]; gr[j].qv[1] = s_grip[9 * TILE + le];
-                    const uint32_t res = s_ctc[le];
-                    ctc[j] = res & 0x7fffu;
-                    priv[j] = (res & 0x80000000u) | (ctc[j] & ~gripper_pair_mask());
-                }
-                fail = env_post_step<ID>(ctc[j], touch_now[j], touch_ever[j], succ[j], tt[j]);
-                done = tt[j] >= kT;
-                n_st += 1.f; r_sum += fail ? -1.f : 0.f;
-                if (p.reward) store_reward(p.reward + row, fail);
-                if (p.success) p.success[row] = (float)succ[j];
-                if (p.done) p.done[row] = done ? 1 : 0;
-            }
-            // observation rows: registers + shared cube state -> stage -> coalesced global stores
-            if (p.obs) {
-                if (live[j]) {
-                    Env<NB> e;
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) { e.g[d] = gr[j].g[d]; e.gv[d] = gr[j].gv[d]; }
-                    e.q[0] = gr[j].q[0]; e.q[1] = gr[j].q[1]; e.qv[0] = gr[j].qv[0]; e.qv[1] = gr[j].qv[1];
-#pragma unroll
-                    for (int b = 0; b < NB; ++b) {
-                        const float* bb = s_blk + (9 * b) * TILE + le;
-                        e.px[b] = bb[0]; e.py[b] = bb[TILE]; e.pz[b] = bb[2 * TILE]; e.c[b] = bb[3 * TILE]; e.s[b] = bb[4 * TILE];
-                        e.vx[b] = bb[5 * TILE]; e.vy[b] = bb[6 * TILE]; e.vz[b] = bb[7 * TILE]; e.w[b] = bb[8 * TILE];
-                    }
-                    e.nb = nb[j];
-                    stage_row<C::DIMO, T::OSTR>(my_stage, lane, [&](auto&& put) { env_write_obs<ID>(e, put); });
-                }
-                __syncwarp();
-                flush_rows<C::DIMO, T::OSTR>(my_stage, p.obs + ((int64_t)k * p.B + rg0) * C::DIMO, nv, lane);
-                __syncwarp();
-            }
-            if (p.ag) {
-                if (live[j]) stage_row<C::DIMG, T::GSTR>(my_stage, lane, [&](auto&& put) { env_write_ag<ID>(touch_now[j], touch_ever[j], put); });
-                __syncwarp();
-                flush_rows<C::DIMG, T::GSTR>(my_stage, p.ag + ((int64_t)k * p.B + rg0) * C::DIMG, nv, lane);
-                __syncwarp();
-            }
-            if (live[j] && done) {
-                n_ep += 1.f; n_su += (float)succ[j];
-                if (p.auto_reset) {
-                    // RobotEnv.reset inside the kernel (rare: once per 50 steps and env)
-                    reset_in_tile<ID>(st, p, p.env0 + li, li, gr[j], s_blk + le, nb[j], touch_now[j], touch_ever[j], priv[j]);
-                    succ[j] = 0; tt[j] = 0;
-                }
-            }
-        }
-        n_inv += (float)inv;
-        // phase C of this step and phase A of the next touch only the owner's own columns of s_blk /
-        // s_grip / s_act, so no barrier is needed here; the two barriers above order the worker accesses.
-    }
-
-    // ---- write the state back
-#pragma unroll
-    for (int j = 0; j < EPT; ++j) {
-        if (!live[j]) continue;
-        const int le = j * T::THREADS + tid;
-        const int64_t gi = p.env0 + tile0 + le;
-        uint32_t* q = st + gi;
-        int f = 0;
-        auto stf = [&](float v) { q[(int64_t)f * p.stateB] = __float_as_uint(v); ++f; };
-        auto stu = [&](uint32_t v) { q[(int64_t)f * p.stateB] = v; ++f; };
-        stf(gr[j].g[0]); stf(gr[j].g[1]); stf(gr[j].g[2]);
-        stf(gr[j].gv[0]); stf(gr[j].gv[1]); stf(gr[j].gv[2]);
-        stf(gr[j].q[0]); stf(gr[j].q[1]); stf(gr[j].qv[0]); stf(gr[j].qv[1]);
-#pragma unroll
-        for (int w = 0; w < 9 * NB; ++w) stf(s_blk[w * TILE + le]);
-        stu(touch_now[j] | (touch_ever[j] << 16));
-        stu((uint32_t)tt[j] | ((uint32_t)succ[j] << 8) | ((uint32_t)nb[j] << 9));
-        stu(priv[j]);
-    }
-    n_ep = warp_sum(n_ep); n_su = warp_sum(n_su); n_st = warp_sum(n_st); n_inv = warp_sum(n_inv); r_sum = warp_sum(r_sum);
-    n_act = warp_sum(n_act);
-    if (lane == 0 && p.stats) {
-        if (n_act != 0.f) atomicAdd(p.stats + BP_STAT_WORKER_STEPS, (double)n_act);
-        if (n_ep != 0.f) atomicAdd(p.stats + BP_STAT_EPISODES, (double)n_ep);
-        if (n_su != 0.f) atomicAdd(p.stats + BP_STAT_SUCCESSES, (double)n_su);
-        if (n_st != 0.f) atomicAdd(p.stats + BP_STAT_STEPS, (double)n_st);
-        if (n_inv != 0.f) atomicAdd(p.stats + BP_STAT_INVALID, (double)n_inv);
-        if (r_sum != 0.f) atomicAdd(p.stats + BP_STAT_REWARD_SUM, (double)r_sum);
-    }
-}
-
-#endif  // BP_EXPERIMENTS
 
 }  // namespace bp
 
@@ -740,49 +394,6 @@ __global__ void compute_reward_kernel(const float* __restrict__ ag, const float*
     store_reward(r + i, d != (float)c);
 }
 
-#ifdef BP_EXPERIMENTS   // the original thread-per-transition relabel kernel (43 % of HBM), superseded by her_sample_kernel
-// HER relabel + reward (baselines.her.her._sample_her_transitions [upstream]; config.py:107-123)
-__global__ void her_relabel_kernel(const float* __restrict__ ep_ag, const float* __restrict__ ep_g, int B, int T, int dimg,
-                                   int64_t n, float future_p, uint32_t k0, uint32_t k1, int64_t index_offset,
-                                   int32_t* ep_idx, int32_t* t_idx, int32_t* fut_t, float* ag2_out, float* g_out, float* r_out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint64_t gi = (uint64_t)(i + index_offset);
-    U4 w = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 3u, 0u, k0, k1);
-    int e = (int)__umulhi(w.x, (uint32_t)B);
-    int t = (int)__umulhi(w.y, (uint32_t)T);
-    bool her = u01(w.z) < future_p;
-    int off = (int)(u01(w.w) * (float)(T - t));
-    int ft = t + 1 + off;
-    const float* ag2 = ep_ag + ((int64_t)e * (T + 1) + (t + 1)) * dimg;
-    const float* gs = her ? ep_ag + ((int64_t)e * (T + 1) + ft) * dimg : ep_g + ((int64_t)e * T + t) * dimg;
-    float d = 0.0f;
-    int c = 0;
-    if ((dimg & 3) == 0) {
-        for (int k = 0; k < dimg / 4; ++k) {
-            float4 x = __ldg(reinterpret_cast<const float4*>(ag2) + k);
-            float4 y = __ldg(reinterpret_cast<const float4*>(gs) + k);
-            d = d + x.x * y.x; d = d + x.y * y.y; d = d + x.z * y.z; d = d + x.w * y.w;
-            c += (y.x != 0.0f) + (y.y != 0.0f) + (y.z != 0.0f) + (y.w != 0.0f);
-            if (g_out) reinterpret_cast<float4*>(g_out + i * dimg)[k] = y;
-            if (ag2_out) reinterpret_cast<float4*>(ag2_out + i * dimg)[k] = x;
-        }
-    } else {
-        for (int k = 0; k < dimg; ++k) {
-            float x = __ldg(ag2 + k), y = __ldg(gs + k);
-            d = d + x * y;
-            c += (y != 0.0f);
-            if (g_out) g_out[i * dimg + k] = y;
-            if (ag2_out) ag2_out[i * dimg + k] = x;
-        }
-    }
-    if (r_out) store_reward(r_out + i, d != (float)c);
-    if (ep_idx) ep_idx[i] = e;
-    if (t_idx) t_idx[i] = t;
-    if (fut_t) fut_t[i] = her ? ft : -1;
-}
-
-#endif  // BP_EXPERIMENTS
 
 }  // namespace bp
 
@@ -876,10 +487,6 @@ static int step_kernel_choice() {
         if (e && strcmp(e, "simple") == 0) return 2;
         if (e && strcmp(e, "async") == 0) return 0;
         if (e && strcmp(e, "split") == 0) return 4;
-#ifdef BP_EXPERIMENTS
-        if (e && strcmp(e, "tiled") == 0) return 1;
-        if (e && strcmp(e, "duo") == 0) return 3;
-#endif
         return 0;   // default: the slab-resident kernel (step_kernel_async); split measured 4.21e9 vs 4.50e9 env-steps/s
     }();
     return v;
@@ -941,29 +548,14 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
         if (choice == 2) {
             constexpr size_t kSmem = sizeof(float) * Col<Cfg<ID>::NB, 128>::kFields * 128;
             step_kernel_simple<ID><<<nblk(a.B, 128), 128, kSmem, s>>>(h->d_state, a);
-#ifdef BP_EXPERIMENTS
-        } else if (choice == 1) {
-            using T = Tile<ID>;
-            static AttrOnce once;
-            if (once.need(h->device)) {
-                int r = set_smem_attr(step_kernel_tiled<ID>, T::SMEM + pad);
-                if (r != BP_OK) return r;
-                once.mark(h->device);
-            }
-            step_kernel_tiled<ID><<<nblk(a.B, T::TILE), T::THREADS, T::SMEM + pad, s>>>(h->d_state, a);
-#endif
         } else {
             // envs per lane (tuning).  Measured at the 18 KB slab, resident warps in brackets: E = 2 [20] 2.22e9, 3 [15] 3.16e9,
             // 4 [12] 3.28e9, 5 [10] 3.23e9, 6 [8] 3.08e9 env-steps/s
             // per id (E = 4 / 3 / 2): GripperTouch 3.78 / 3.97 / 3.83e9, ToppleTower 1.32 / 1.34 / 1.22e9, Variation 1.42 / 1.46 / 1.41e9
             static const int e_env = [] { const char* e = getenv("BP_ASYNC_E"); return e ? atoi(e) : 0; }();
             const int e_def = (ID == 0 || ID == 2 || ID == 6) ? 3 : kAsyncE;
-#ifdef BP_EXPERIMENTS
-            const int e_sel = e_env ? e_env : e_def;
-#else
             const int e_sel = e_def;   // other E are only instantiated in the experiments build
             (void)e_env;
-#endif
             // the lean instantiation serves the plain fused step (see step_kernel_async)
             const bool lean = a.layout == 0 && a.actions && !a.actions_out && !a.done && !a.goal_out && !a.reset_obs && !a.reset_ag;
             auto go = [&](auto ec, auto lc) -> int {
@@ -973,9 +565,6 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                 static AttrOnce once;
                 if (once.need(h->device)) {
                     int r = set_smem_attr(step_kernel_async<ID, E, LEAN>, A::SMEM + pad);
-#ifdef BP_EXPERIMENTS
-                    if (r == BP_OK) r = set_smem_attr(step_kernel_duo<ID, E>, Duo<ID, E>::SMEM + pad);
-#endif
                     if (r != BP_OK) return r;
                     once.mark(h->device);
                 }
@@ -994,20 +583,13 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                     c.K = (a.K - k0) < kMaxFused ? (a.K - k0) : kMaxFused;
                     c.k0 = a.k0 + k0;
                     c.act_k0 = a.act_k0 + k0;
-#ifdef BP_EXPERIMENTS
-                    if (choice == 3) { step_kernel_duo<ID, E><<<nblk(a.B, A::CS), 64, Duo<ID, E>::SMEM + pad, s>>>(h->d_state, c); continue; }
-#endif
                     step_kernel_async<ID, E, LEAN><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
                 }
                 return (int)BP_OK;
             };
             using T_ = std::true_type; using F_ = std::false_type;
             auto go_e = [&](auto ec) -> int { return lean ? go(ec, T_()) : go(ec, F_()); };
-#ifdef BP_EXPERIMENTS
-            int r = e_sel == 2 ? go_e(std::integral_constant<int, 2>()) : e_sel == 3 ? go_e(std::integral_constant<int, 3>()) : go_e(std::integral_constant<int, 4>());
-#else
             int r = go_e(std::integral_constant<int, ((ID == 0 || ID == 2 || ID == 6) ? 3 : kAsyncE)>());
-#endif
             if (r != BP_OK) return r;
         }
         return (int)BP_OK;
@@ -1420,16 +1002,6 @@ int bp_her_relabel(const float* d_ep_ag, const float* d_ep_g, int32_t B, int32_t
     if (n == 0) return BP_OK;
     if (!d_ep_ag || !d_ep_g) return fail(BP_ERR_INVALID_ARG, "null episode store");
     // the goal / reward subset of the transition sampler: same draw, same kernel (block-cooperative row gathers)
-#ifdef BP_EXPERIMENTS
-    static const bool legacy = [] { const char* e = getenv("BP_HER_RELABEL_LEGACY"); return e && atoi(e) != 0; }();
-    if (legacy) {
-        her_relabel_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(d_ep_ag, d_ep_g, B, T, dimg, n, future_p,
-                                                                          (uint32_t)seed, (uint32_t)(seed >> 32), index_offset,
-                                                                          d_ep_idx, d_t, d_future_t, d_ag2, d_g, d_r);
-        CU(cudaGetLastError());
-        return BP_OK;
-    }
-#endif
     if (dimg > 256) return fail(BP_ERR_INVALID_ARG, "dimg > 256 is not supported (the registered ids have dimg <= 36)");
     return bp_her_sample(nullptr, nullptr, d_ep_g, d_ep_ag, nullptr, B, T, 1, 0, dimg, n, future_p, 0.0f, seed, index_offset,
                          d_ep_idx, d_t, d_future_t, nullptr, nullptr, nullptr, d_g, nullptr, d_ag2, d_r, nullptr, nullptr, stream);

@@ -130,16 +130,8 @@ __global__ void __launch_bounds__(kSplitQuietThreads) split_quiet_kernel(uint32_
             g2.q[0] = e.q[0]; g2.q[1] = e.q[1]; g2.qv[0] = e.qv[0]; g2.qv[1] = e.qv[1];
             float m[3], ctrl[2];
             action_targets<C::BG>(g2, a, m, ctrl);
-            float lo[3] = {g2.g[0], g2.g[1], g2.g[2]}, hi[3] = {g2.g[0], g2.g[1], g2.g[2]};
-            float qmax = fmaxf(g2.q[0], g2.q[1]);
-#pragma unroll 1
-            for (int sub = 0; sub < kNSub; ++sub) {
-                GripSub gs;
-                substep_gripper<C::BG>(g2, gs, m, ctrl);
-#pragma unroll
-                for (int d = 0; d < 3; ++d) { lo[d] = fminf(lo[d], g2.g[d]); hi[d] = fmaxf(hi[d], g2.g[d]); }
-                if (!C::BG) qmax = fmaxf(qmax, fmaxf(g2.q[0], g2.q[1]));
-            }
+            float lo[3], hi[3], qmax;
+            quiet_gripper_step<C::BG>(g2, m, ctrl, lo, hi, qmax);
             quiet = true;
 #pragma unroll
             for (int b = 0; b < NB; ++b)

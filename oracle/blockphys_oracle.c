@@ -18,6 +18,7 @@
  *   __init__.py:6-53             ids, max_episode_steps = 50
  */
 #include "blockphys_oracle.h"
+#include "blockphys_tables.h"
 
 #include <math.h>
 #include <string.h>
@@ -357,6 +358,18 @@ typedef struct {
     float closed[2];
 } sub_tmp;
 
+/* BlockPhys v2: the env-step's propagator base.  The weld and the finger actuators are linear, so until a contact
+ * acts on a channel its state after n substeps is the n-th power of the substep map (blockphys_tables.h) applied to
+ * the state the env-step started from: d0 / e0 = position - target, v0 / w0 = velocity.  x and y are never acted on.
+ * The z channel leaves this "free" mode when a finger lands on a cube, a finger channel when its closing is undone
+ * (collide_finger_block); from then on that channel advances by the substep recurrence of v1. */
+typedef struct {
+    float d0[3], v0[3]; /* gripper */
+    float e0[2], w0[2]; /* fingers */
+    int zfree, qfree[2];
+    int n;              /* current substep, 1..NSUB */
+} step_base;
+
 static void finger_rect(const bpo_sim* sim, int f, rect2* r, float* z) {
     float sgn = f == 0 ? 1.0f : -1.0f;
     r->x = sim->g[0];
@@ -366,7 +379,7 @@ static void finger_rect(const bpo_sim* sim, int f, rect2* r, float* z) {
     *z = sim->g[2] + FZ_OFF;
 }
 
-static void collide_finger_block(bpo_sim* sim, int f, int bi, sub_tmp* st) {
+static void collide_finger_block(bpo_sim* sim, int f, int bi, sub_tmp* st, step_base* sb) {
     float* closed = st->closed;
     blk_tmp* tmp = st->b;
     bpo_block* b = &sim->blk[bi];
@@ -390,6 +403,10 @@ static void collide_finger_block(bpo_sim* sim, int f, int bi, sub_tmp* st) {
             tmp[bi].supported = 1;
         } else {          /* finger rests on the block: the gripper yields upward */
             sim->g[2] = (b->pos[2] + (FZ + HB)) - FZ_OFF;
+            if (sb->zfree) { /* v2: the z channel leaves the propagator with the velocity it has there now */
+                sim->gv[2] = F(BPO_GC[sb->n], sb->d0[2], BPO_GD[sb->n] * sb->v0[2]);
+                sb->zfree = 0;
+            }
             if (sim->gv[2] < 0.0f) sim->gv[2] = 0.0f;
         }
         return;
@@ -406,6 +423,7 @@ static void collide_finger_block(bpo_sim* sim, int f, int bi, sub_tmp* st) {
             if (yield > 0.0f) {
                 sim->q[f] = sim->q[f] + yield;
                 sim->qv[f] = 0.0f;
+                sb->qfree[f] = 0; /* v2: this finger advances by the recurrence for the rest of the env-step */
                 closed[f] = closed[f] - yield;
                 delta = delta - yield;
             }
@@ -496,32 +514,46 @@ static int over_table(float x, float y) {
     return fabsf(x - TBL_X) <= TBL_HX && fabsf(y - TBL_Y) <= TBL_HY;
 }
 
-void bpo_sim_substep(bpo_sim* sim) {
+static void sim_substep(bpo_sim* sim, step_base* sb) {
     sub_tmp st;
     blk_tmp* tmp = st.b;
     float* closed = st.closed;
+    const int n = sb->n;
     closed[0] = closed[1] = 0.0f;
     st.g_old[0] = sim->g[0]; st.g_old[1] = sim->g[1]; st.g_old[2] = sim->g[2];
     st.q_old[0] = sim->q[0]; st.q_old[1] = sim->q[1];
-    /* 1. gripper: critically damped tracking of the mocap target (weld, shared.xml:48-50) */
-    for (int k = 0; k < 3; ++k) {
-        float acc = F(KW, sim->m[k] - sim->g[k], -(BW * sim->gv[k]));
-        sim->gv[k] = F(acc, H, sim->gv[k]);
-        sim->g[k] = F(sim->gv[k], H, sim->g[k]);
+    /* 1. gripper: critically damped tracking of the mocap target (weld, shared.xml:48-50).
+     * v2: x and y are the propagator applied to the env-step's start state (their velocities are only needed at the
+     * end of the env-step, bpo_sim_step); z likewise while it is free, projected onto z >= GZ_MIN (the finger
+     * bottoms on the table: a position projection inside the env-step, the velocity rule is applied at its end). */
+    for (int k = 0; k < 2; ++k) sim->g[k] = F(BPO_GA[n], sb->d0[k], F(BPO_GB[n], sb->v0[k], sim->m[k]));
+    if (sb->zfree) {
+        float zv = F(BPO_GA[n], sb->d0[2], F(BPO_GB[n], sb->v0[2], sim->m[2]));
+        sim->g[2] = zv < GZ_MIN ? GZ_MIN : zv;
+    } else {
+        float acc = F(KW, sim->m[2] - sim->g[2], -(BW * sim->gv[2]));
+        sim->gv[2] = F(acc, H, sim->gv[2]);
+        sim->g[2] = F(sim->gv[2], H, sim->g[2]);
+        if (sim->g[2] < GZ_MIN) {
+            sim->g[2] = GZ_MIN;
+            if (sim->gv[2] < 0.0f) sim->gv[2] = 0.0f;
+        }
     }
-    if (sim->g[2] < GZ_MIN) {
-        sim->g[2] = GZ_MIN;
-        if (sim->gv[2] < 0.0f) sim->gv[2] = 0.0f;
-    }
-    /* 2. fingers: position actuators (2blocks.xml:39-42); block_gripper pins them at 0 (fetch_env.py:149-152) */
+    /* 2. fingers: position actuators (2blocks.xml:39-42); block_gripper pins them at 0 (fetch_env.py:149-152).
+     * v2: free fingers follow the propagator, projected onto the joint range [0, QMAX]. */
     if (!sim->block_gripper) {
         for (int f = 0; f < 2; ++f) {
             float q_old = sim->q[f];
-            float acc = F(KF, sim->ctrl[f] - sim->q[f], -(BF * sim->qv[f]));
-            sim->qv[f] = F(acc, H, sim->qv[f]);
-            sim->q[f] = F(sim->qv[f], H, sim->q[f]);
-            if (sim->q[f] < 0.0f) { sim->q[f] = 0.0f; if (sim->qv[f] < 0.0f) sim->qv[f] = 0.0f; }
-            if (sim->q[f] > QMAX) { sim->q[f] = QMAX; if (sim->qv[f] > 0.0f) sim->qv[f] = 0.0f; }
+            if (sb->qfree[f]) {
+                float qv = F(BPO_FA[n], sb->e0[f], F(BPO_FB[n], sb->w0[f], sim->ctrl[f]));
+                sim->q[f] = clampf(qv, 0.0f, QMAX);
+            } else {
+                float acc = F(KF, sim->ctrl[f] - sim->q[f], -(BF * sim->qv[f]));
+                sim->qv[f] = F(acc, H, sim->qv[f]);
+                sim->q[f] = F(sim->qv[f], H, sim->q[f]);
+                if (sim->q[f] < 0.0f) { sim->q[f] = 0.0f; if (sim->qv[f] < 0.0f) sim->qv[f] = 0.0f; }
+                if (sim->q[f] > QMAX) { sim->q[f] = QMAX; if (sim->qv[f] > 0.0f) sim->qv[f] = 0.0f; }
+            }
             float cl = q_old - sim->q[f];
             closed[f] = cl > 0.0f ? cl : 0.0f;
         }
@@ -557,7 +589,7 @@ void bpo_sim_substep(bpo_sim* sim) {
     /* 4b. fingers vs cubes */
     for (int i = 0; i < sim->nblocks; ++i)
         for (int f = 0; f < 2; ++f)
-            collide_finger_block(sim, f, i, &st);
+            collide_finger_block(sim, f, i, &st, sb);
     /* 4c. cube pairs */
     for (int i = 0; i < sim->nblocks; ++i)
         for (int j = i + 1; j < sim->nblocks; ++j)
@@ -589,8 +621,29 @@ void bpo_sim_substep(bpo_sim* sim) {
     }
 }
 
+/* sim.step() (robot_env.py:60): NSUB substeps towards the targets set_action / set_targets left in m, ctrl */
 void bpo_sim_step(bpo_sim* sim) {
-    for (int i = 0; i < NSUB; ++i) bpo_sim_substep(sim);
+    step_base sb;
+    for (int k = 0; k < 3; ++k) { sb.d0[k] = sim->g[k] - sim->m[k]; sb.v0[k] = sim->gv[k]; }
+    for (int f = 0; f < 2; ++f) { sb.e0[f] = sim->q[f] - sim->ctrl[f]; sb.w0[f] = sim->qv[f]; }
+    sb.zfree = 1; sb.qfree[0] = sb.qfree[1] = 1;
+    for (sb.n = 1; sb.n <= NSUB; ++sb.n) sim_substep(sim, &sb);
+    /* end of the env-step: velocities of the channels that stayed free, with the limit rules of v1 applied once */
+    for (int k = 0; k < 2; ++k) sim->gv[k] = F(BPO_GC[NSUB], sb.d0[k], BPO_GD[NSUB] * sb.v0[k]);
+    if (sb.zfree) {
+        float zv = F(BPO_GA[NSUB], sb.d0[2], F(BPO_GB[NSUB], sb.v0[2], sim->m[2]));
+        sim->gv[2] = F(BPO_GC[NSUB], sb.d0[2], BPO_GD[NSUB] * sb.v0[2]);
+        if (zv < GZ_MIN && sim->gv[2] < 0.0f) sim->gv[2] = 0.0f;
+    }
+    if (!sim->block_gripper) {
+        for (int f = 0; f < 2; ++f) {
+            if (!sb.qfree[f]) continue;
+            float qv = F(BPO_FA[NSUB], sb.e0[f], F(BPO_FB[NSUB], sb.w0[f], sim->ctrl[f]));
+            sim->qv[f] = F(BPO_FC[NSUB], sb.e0[f], BPO_FD[NSUB] * sb.w0[f]);
+            if (qv < 0.0f && sim->qv[f] < 0.0f) sim->qv[f] = 0.0f;
+            if (qv > QMAX && sim->qv[f] > 0.0f) sim->qv[f] = 0.0f;
+        }
+    }
 }
 
 /* ======================================================================

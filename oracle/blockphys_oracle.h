@@ -137,7 +137,6 @@ void bpo_sim_init(bpo_sim* sim, int env_id);       /* initial_state, robot_env.p
 void bpo_sim_set_action(bpo_sim* sim, const float a[4]); /* fetch_env.py:170-185 (after clip) */
 /* the same targets from what upstream utils.mocap_set_action / ctrl_set_action write (float64 mocap_pos, ctrl) */
 void bpo_sim_set_targets(bpo_sim* sim, const double mocap_pos[3], const double ctrl[2]);
-void bpo_sim_substep(bpo_sim* sim);
 void bpo_sim_step(bpo_sim* sim);                   /* 20 substeps, robot_env.py:60 */
 int bpo_pair_index(int o1, int o2);
 

@@ -108,7 +108,6 @@ def lib():
         L.bpo_sim_set_action.argtypes = [vp, vp]
         L.bpo_sim_set_targets.argtypes = [vp, vp, vp]
         L.bpo_sim_step.argtypes = [vp]
-        L.bpo_sim_substep.argtypes = [vp]
         assert L.bpo_sizeof_state() == STATE_DTYPE.itemsize, (L.bpo_sizeof_state(), STATE_DTYPE.itemsize)
         _lib = L
     return _lib

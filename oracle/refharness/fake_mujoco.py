@@ -302,8 +302,9 @@ class MjSim(object):
             ctrl_by_joint = dict(zip(self.model.actuator_joint, self.data.ctrl))
             ctrl = (C.c_double * 2)(float(ctrl_by_joint["robot0:r_gripper_finger_joint"]), float(ctrl_by_joint["robot0:l_gripper_finger_joint"]))
             self.L.bpo_sim_set_targets(C.byref(s), m, ctrl)
-            for _ in range(self.nsubsteps):
-                self.L.bpo_sim_substep(C.byref(s))
+            # BlockPhys v2 propagates a whole env-step (its tables cover the 20 substeps tasks.py:16 asks for)
+            assert self.nsubsteps == 20, self.nsubsteps
+            self.L.bpo_sim_step(C.byref(s))
         self.data.time += self.nsubsteps * self.model.opt.timestep
         self.forward()
         # the contact list of the last substep (sim.data.contact / ncon)
