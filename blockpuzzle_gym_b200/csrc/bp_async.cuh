@@ -30,18 +30,27 @@ struct Async {
     using C = Cfg<ID>;
     static constexpr int NB = C::NB;
     static constexpr int CS = 32 * E;                       // envs per warp = column stride of the slab
-    static constexpr int W_CUB = 9 * NB * CS, W_GRP = 10 * CS, W_MSC = 3 * CS;
+    static constexpr int W_GRP = 10 * CS, W_MSC = 3 * CS;
     // ids with three or four cubes keep round 1's pass (cubes stepped in place in the slab through shared-memory
     // loops, 4 words of per-lane scratch per cube): unrolled over 4 cubes, 8 finger slots and 6 pairs the register
     // form is 74-91 KB of SASS and measured 13-23 % slower there (ToppleTower 1.32 -> 1.01e9, Variation 1.41 -> 1.22e9)
     static constexpr bool REG_PASS = NB <= 2;
+    // yaw cache (ids with the register pass): the yaw observation of every cube, bp_atan2(s, c), kept as a tenth column
+    // per cube behind the nine state columns and refreshed only when the cube may have turned (slab load, reset, full-
+    // physics pass).  _get_obs evaluated it for every cube at every env-step: 5.6 % of the kernel's instructions incl. the
+    // division slow path, and 4 KB of the hot code.  One more KB of slab: 11 instead of 12 resident warps, measured neutral.
+    static constexpr bool YAW = REG_PASS;
+    static constexpr int W_CUB = (9 * NB + (YAW ? NB : 0)) * CS;
     static constexpr int W_COL = REG_PASS ? 0 : Col<NB, CS, 32>::kScratch * 32;
     static constexpr int W_PEND = CS;                        // two uint16 rings of CS entries: pending full-physics env-steps, pending resets
     static constexpr int W_BITS = kMaxFused * E;             // reward bits of every (step, env) of the launch
     static constexpr size_t SMEM = sizeof(uint32_t) * (size_t)(W_CUB + W_GRP + W_MSC + W_COL + W_PEND + W_BITS);
 };
 
-constexpr int kAsyncE = 4;  // envs per lane
+#ifndef BP_ASYNC_E
+#define BP_ASYNC_E 4
+#endif
+constexpr int kAsyncE = BP_ASYNC_E;  // envs per lane (build-time; -DBP_ASYNC_E for sweeps)
 constexpr int kTuneForceFull = 1 << 23;   // StepArgs::tune: skip the quiet path (measurement of the all-full-physics floor)
 
 // The slab's three bookkeeping words per env: [0] touch masks (now | ever << 16), [1] kernel-private flags
@@ -51,6 +60,13 @@ constexpr uint32_t kPendingBit = 1u << 16;
 constexpr uint32_t kPrivMask = 0x80007fffu;
 __device__ __forceinline__ uint32_t pf_flags(uint32_t pf) { return (pf >> 16) & 0xfffu; }
 __device__ __forceinline__ uint32_t pf_make(uint32_t priv, uint32_t flags) { return (priv & kPrivMask) | (flags << 16); }
+
+// refresh the yaw cache of one slab column (see Async::YAW); one out-of-line copy serves all call sites
+template <int NB, int CS>
+__device__ __noinline__ void yaw_refresh(float* cub) {
+#pragma unroll 1
+    for (int b = 0; b < NB; ++b) cub[(9 * NB + b) * CS] = bp_atan2(cub[(9 * b + 4) * CS], cub[(9 * b + 3) * CS]);
+}
 
 // RobotEnv.reset for one env of a slab (rare and large: kept out of line)
 template <int ID, int CS, bool LEAN>
@@ -78,6 +94,7 @@ __device__ __noinline__ void reset_env_slab(uint32_t* __restrict__ st, const Ste
         bb[0] = e.px[b]; bb[CS] = e.py[b]; bb[2 * CS] = e.pz[b]; bb[3 * CS] = e.c[b]; bb[4 * CS] = e.s[b];
         bb[5 * CS] = e.vx[b]; bb[6 * CS] = e.vy[b]; bb[7 * CS] = e.vz[b]; bb[8 * CS] = e.w[b];
     }
+    if (Async<ID, CS / 32>::YAW) yaw_refresh<NB, CS>(cub);
     msc[0] = e.touch_now | (e.touch_ever << 16);
     msc[CS] = pf_make(e.priv, (uint32_t)e.t | ((uint32_t)e.succ << 8) | ((uint32_t)e.nb << 9));
     if (!LEAN) {
@@ -139,7 +156,11 @@ __device__ __noinline__ uint32_t finalize_step(uint32_t contacts, float* cub, fl
             e.vx[b] = bb[5 * CS]; e.vy[b] = bb[6 * CS]; e.vz[b] = bb[7 * CS]; e.w[b] = bb[8 * CS];
         }
         e.nb = nb;
-        store_row<C::DIMO>(obs_row_p, [&](auto&& put) { env_write_obs<ID>(e, put); });
+        constexpr bool YAW = Async<ID, CS / 32>::YAW;
+        float yw[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) yw[b] = YAW ? cub[(9 * NB + b) * CS] : 0.0f;
+        store_row<C::DIMO>(obs_row_p, [&](auto&& put) { env_write_obs<ID>(e, put, YAW ? yw : nullptr); });
     }
     if (ag_row_p) store_row<C::DIMG>(ag_row_p, [&](auto&& put) { env_write_ag<ID>(touch_now, touch_ever, put); });
     return (fail ? 1u : 0u) | (done ? 2u : 0u) | ((done && succ) ? 4u : 0u);
@@ -268,6 +289,7 @@ __device__ __forceinline__ uint32_t full_step_item(uint32_t* __restrict__ st, co
             bb[0] = q.x[b]; bb[CS] = q.y[b]; bb[2 * CS] = q.z[b]; bb[3 * CS] = q.c[b]; bb[4 * CS] = q.s[b];
             bb[5 * CS] = q.vx[b]; bb[6 * CS] = q.vy[b]; bb[7 * CS] = q.vz[b]; bb[8 * CS] = q.w[b];
         }
+        if (Async<ID, E>::YAW) yaw_refresh<NB, CS>(s_cub + pw);
     } else {
         is_static = sim_step_col<NB, CS, C::BG>(g, a, Col<NB, CS, 32>(s_cub + pw, s_scr), (int)((flags >> 9) & 7u), contacts);
     }
@@ -316,6 +338,7 @@ __device__ __forceinline__ uint32_t slab_load(const uint32_t* __restrict__ st, c
         for (int d = 0; d < 10; ++d) s_grp[d * CS + w] = __uint_as_float(q[(int64_t)d * p.stateB]);
 #pragma unroll 1
         for (int d = 0; d < 9 * NB; ++d) s_cub[d * CS + w] = __uint_as_float(q[(int64_t)(10 + d) * p.stateB]);
+        if (Async<ID, E>::YAW) yaw_refresh<NB, CS>(s_cub + w);
         int f = 10 + 9 * NB;
         s_msc[w] = q[(int64_t)f * p.stateB]; ++f;                        // touch
         const uint32_t flags = q[(int64_t)f * p.stateB]; ++f;

@@ -136,7 +136,10 @@ __device__ __forceinline__ float bp_atan2(float s, float c) {
     float mx = as > ac ? as : ac;
     float mn = as > ac ? ac : as;
     if (mx == 0.0f) return 0.0f;
-    float a = mn / mx;
+    // 0 / mx is +0 exactly; dividing mx / mx instead keeps the zero numerator (a never-turned cube: s = 0) away from the
+    // IEEE division's slow path, which the hardware check sends every zero operand through (same result bits)
+    float a = (mn == 0.0f ? mx : mn) / mx;
+    a = mn == 0.0f ? 0.0f : a;
     float off = 0.0f;
     if (a > 0.41421357f) {
         a = (a - 1.0f) / (a + 1.0f);
@@ -1137,7 +1140,7 @@ __device__ __forceinline__ float ag_value(uint32_t now, uint32_t ever, int i, in
 
 // _get_obs (fetch_env.py:187-228; Variation :567-621) into a row of DIMO floats with stride `os`
 template <int ID, typename Store>
-__device__ __forceinline__ void env_write_obs(const Env<Cfg<ID>::NB>& e, Store&& put) {
+__device__ __forceinline__ void env_write_obs(const Env<Cfg<ID>::NB>& e, Store&& put, const float* yaw = nullptr) {
     using C = Cfg<ID>;
     constexpr int NB = C::NB;
     float gvp0 = e.gv[0] * kDt, gvp1 = e.gv[1] * kDt, gvp2 = e.gv[2] * kDt;
@@ -1159,7 +1162,7 @@ __device__ __forceinline__ void env_write_obs(const Env<Cfg<ID>::NB>& e, Store&&
         put(o + 5, live ? e.pz[i] - e.g[2] : 0.0f);
         put(o + 6, live ? __uint_as_float(0x80000000u) : 0.0f);   // roll: mat2euler gives -arctan2(0, 1) = -0.0 (fetch_env.py:205)
         put(o + 7, 0.0f);
-        put(o + 8, live ? bp_atan2(e.s[i], e.c[i]) : 0.0f);
+        put(o + 8, live ? (yaw ? yaw[i] : bp_atan2(e.s[i], e.c[i])) : 0.0f);   // yaw: the caller's cached bp_atan2(s, c), if it keeps one
         put(o + 9, live ? e.vx[i] * kDt - gvp0 : 0.0f);
         put(o + 10, live ? e.vy[i] * kDt - gvp1 : 0.0f);
         put(o + 11, live ? e.vz[i] * kDt - gvp2 : 0.0f);
