@@ -165,7 +165,7 @@ struct StepArgs {
     int act_k0;            // row of `actions` that holds step k0's actions (== k0, or 0 for the per-step tensor of bp_rollout_step)
     int Ktot;
     float* goal_out;       // layout 1: desired_goal rows [B][Ktot][DIMG] (nullable)
-    int tune;              // duo kernel: minimum ready lanes for a scheduler iteration while the worker is busy
+    int tune;              // async kernel: queue thresholds (see launch_step) | kTuneForceFull
 };
 
 __device__ __forceinline__ int64_t step_row(const StepArgs& p, int k, int64_t li) {
@@ -524,11 +524,12 @@ static int launch_step_split(bp_handle* h, StepArgs& a, cudaStream_t s) {
     a.tune = h->force_full ? kTuneForceFull : 0;
     int rc = dispatch(h->env_id, [&](auto id) {
         constexpr int ID = decltype(id)::value;
+        static const int skip = [] { const char* e = getenv("BP_SPLIT_SKIP"); return e ? atoi(e) : 0; }();   // timing experiments only
         for (int k = 0; k < a.K; ++k) {
             const int set = k & 1;
-            split_quiet_kernel<ID><<<q_blocks, kSplitQuietThreads, 0, s>>>(h->d_state, a, k, sb, set);
-            split_full_kernel<ID><<<kSplitFullBlocks, kSplitFullThreads, 0, s>>>(h->d_state, a, k, sb, set);
-            split_reset_kernel<ID><<<kSplitResetBlocks, 128, 0, s>>>(h->d_state, a, sb, set);
+            if (!(skip & 1)) split_quiet_kernel<ID><<<q_blocks, kSplitQuietThreads, 0, s>>>(h->d_state, a, k, sb, set);
+            if (!(skip & 2)) split_full_kernel<ID><<<kSplitFullBlocks, kSplitFullThreads, 0, s>>>(h->d_state, a, k, sb, set);
+            if (!(skip & 4)) split_reset_kernel<ID><<<kSplitResetBlocks, 128, 0, s>>>(h->d_state, a, sb, set);
         }
         return (int)BP_OK;
     });
@@ -543,8 +544,8 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
     static const size_t pad = [] { const char* e = getenv("BP_SMEM_PAD"); return e ? (size_t)atoi(e) : (size_t)0; }();  // occupancy experiments
     int rc = dispatch(h->env_id, [&](auto id) {
         constexpr int ID = decltype(id)::value;
-        const int choice = step_kernel_choice();
-        if (a.layout != 0 && choice != 0 && choice != 3) return fail(BP_ERR_INVALID_ARG, "the batch-major episode layout needs the async step kernel");
+        const int choice = h->step_kernel >= 0 ? h->step_kernel : step_kernel_choice();
+        if (a.layout != 0 && choice != 0) return fail(BP_ERR_INVALID_ARG, "the batch-major episode layout needs the async step kernel");
         if (choice == 2) {
             constexpr size_t kSmem = sizeof(float) * Col<Cfg<ID>::NB, 128>::kFields * 128;
             step_kernel_simple<ID><<<nblk(a.B, 128), 128, kSmem, s>>>(h->d_state, a);
@@ -569,13 +570,12 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                     once.mark(h->device);
                 }
                 // the kernel keeps the reward / success bits of at most kMaxFused steps on chip: split longer K
-                // async: reset-pass threshold | full-physics-pass threshold << 8; duo: minimum ready lanes (tuning knobs)
-                static const int tune = [choice] {
-                    if (choice == 3) { const char* e = getenv("BP_DUO_MIN_READY"); return e ? atoi(e) : 32; }
+                // reset-pass threshold | full-physics-pass threshold << 8 | fill rule (tuning knobs)
+                static const int tune = [] {
                     const char* r = getenv("BP_RESET_MIN"); const char* q = getenv("BP_PASS_MIN");
                     const char* fr = getenv("BP_FILL_RULE");   // margin of the fill-comparison pass trigger, -1: off
                     const int frv = fr ? atoi(fr) : 8;
-                    return (r ? atoi(r) : 32) | ((q ? atoi(q) : 24) << 8) | (frv >= 0 ? (1 << 16) | (frv << 17) : 0);   // measured (round 2, lean kernel): reset 4 / 32 -> 4.33 / 4.48e9 at pass 24; pass 20 / 24 / 28 -> 4.44 / 4.48 / 4.46e9 (every reset pass streams ~12 KB of cold code through the instruction cache)
+                    return (r ? atoi(r) : 32) | ((q ? atoi(q) : 28) << 8) | (frv >= 0 ? (1 << 16) | (frv << 17) : 0);   // measured (round 2, lean kernel): reset 4 / 32 -> 4.33 / 4.48e9 at pass 24; pass 20 / 24 / 28 -> 4.44 / 4.48 / 4.46e9 (every reset pass streams ~12 KB of cold code through the instruction cache); BlockPhys v2 kernel: pass 16 / 20 / 24 / 28 / 32 -> 4.48 / 4.74 / 4.86 / 4.92 / 4.84e9
                 }();
                 for (int k0 = 0; k0 < a.K; k0 += kMaxFused) {
                     StepArgs c = a;

@@ -46,3 +46,28 @@ class QuietLogger(object):
 def fake_pg_self(env_name):
     """`self` for calling policy_gradient RolloutStudent.trim (rollout.py:105-171) straight from its source."""
     return types.SimpleNamespace(kwargs={"info": {"env_name": env_name}})
+
+
+# ---- BlockPhys v2 channel events (DESIGN.md section 3): scripted episodes that make a finger land on a cube (the z
+# channel leaves the propagator: "lift") and close the fingers on a cube (the finger channels leave it: "closing undone")
+def grasp_and_land_actions(ref, steps=36):
+    """Closed-loop on an OracleVecEnv (BlocksTouch-v0): even envs descend with CLOSED fingers onto cube 0 (the fingers
+    land on its top face), odd envs open the fingers, descend around cube 0 and close them on it.  Returns the actions
+    [steps][B][4] and the per-step oracle outputs."""
+    import numpy as np
+    B = ref.n
+    acts, outs = [], []
+    for t in range(steps):
+        st = ref.get_state()
+        gp, cube = st["grip_pos"], st["blk_pos"][:, 0]
+        a = np.zeros((B, 4), np.float32)
+        dxy = (cube[:, :2] - gp[:, :2]) / 0.05
+        a[:, :2] = dxy / np.maximum(1.0, np.abs(dxy).max(axis=1, keepdims=True))
+        near = np.abs(cube[:, :2] - gp[:, :2]).max(axis=1) < 0.004
+        land = (np.arange(B) % 2) == 0
+        # land: fingers closed, go down once above the cube.  grasp: fingers open on the way, closed from step 22 on
+        a[:, 2] = np.where(near, -1.0, np.clip((0.60 - gp[:, 2]) / 0.05, -1, 1))
+        a[:, 3] = np.where(land, -1.0, 1.0 if t < 22 else -1.0)
+        acts.append(a)
+        outs.append(ref.step(a))
+    return np.stack(acts), outs

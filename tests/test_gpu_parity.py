@@ -417,6 +417,36 @@ def test_scripted_push_policy_at_scale_matches_oracle():
         assert torch.equal(out[k], out3[k]), k
 
 
+def test_v2_channel_events_match_oracle_on_every_step_kernel():
+    """BlockPhys v2: the gripper z channel and the finger channels follow the tabulated propagator
+    until a contact acts on them.  tests/ref_callers_common.grasp_and_land_actions drives both events on the oracle (a
+    finger landing on a cube; fingers closing on a cube -- asserted there and in tests/test_oracle_cpu.py); the recorded
+    actions replayed by the async, split and simple kernels and with the quiet path disabled: every output bit-identical."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ref_callers_common as rc
+    B = 256
+    env, ref = _make("BlocksTouch-v0", B, seed=11)
+    ref.reset()
+    acts, outs = rc.grasp_and_land_actions(ref)
+    land = (np.arange(B) % 2) == 0
+    st = ref.get_state()
+    assert np.mean(np.abs(st["grip_pos"][land, 2] - 0.5285) < 1e-6) > 0.9 and np.mean(np.abs(st["finger_q"][~land] - 0.0241).max(axis=1) < 2e-4) > 0.9
+    a = torch.from_numpy(acts).cuda()
+    for opt in ({}, {"force_full_physics": 1}, {"step_kernel": 4}, {"step_kernel": 2}):
+        e2, _ = _make("BlocksTouch-v0", B, seed=11)
+        for k, v in opt.items():
+            e2.set_option(k, v)
+        e2.reset()
+        out = e2.step_fused(a, auto_reset=False)
+        for t in range(acts.shape[0]):
+            o, ag, r, s, _, _ = outs[t]
+            assert np.array_equal(out["observation"][t].cpu().numpy().view(np.uint32), o.view(np.uint32)), (opt, t)
+            assert np.array_equal(out["achieved_goal"][t].cpu().numpy(), ag), (opt, t)
+            assert np.array_equal(out["reward"][t].cpu().numpy().view(np.uint32), r.view(np.uint32)), (opt, t)
+        _assert_state_equal(e2, ref, f"after the land / grasp episode with {opt}")
+
+
 @pytest.mark.parametrize("name,obj_range", [("GripperTouch-v0", 0.05), ("ToppleTower-v0", 0.06)])
 def test_spawn_rejection_loop_cap(name, obj_range):
     """the 10 000-attempt cap of the spawn loops.  With obj_range < 0.1 / sqrt(2) the reference's

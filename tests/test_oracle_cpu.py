@@ -3,6 +3,7 @@ the Python restatement against the C restatement, golden fixtures, and physics i
 import ctypes as C
 import math
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -310,3 +311,44 @@ def test_scripted_push_makes_blocks_touch():
         return touched
 
     assert sum(run(s) for s in range(16)) >= 12
+
+
+def test_propagator_tables_are_generated_and_identical_on_both_sides():
+    """BlockPhys v2: oracle/blockphys_tables.h and blockpuzzle_gym_b200/csrc/bp_tables.cuh are the exact powers of the
+    substep map, rounded to binary32, written by tools/gen_blockphys_tables.py -- both files are re-rendered and
+    compared byte for byte, and the 20th power is checked against 20 applications of the float64 recurrence."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_tables", os.path.join(root, "tools", "gen_blockphys_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    for kind, path in gen.OUT.items():
+        assert open(path).read() == gen.render(kind), path
+    t = gen.tables()
+    for (K, B, pre) in ((2500.0, 100.0, "G"), (30000.0 / 104.0, 1000.0 / 104.0, "F")):
+        h = 0.002
+        for d0, v0 in ((1.0, 0.0), (0.0, 1.0)):
+            d, v = d0, v0
+            for _ in range(20):
+                v = v + h * (-K * d - B * v)
+                d = d + h * v
+            a, c = (t[pre + "A"][20], t[pre + "C"][20]) if d0 else (t[pre + "B"][20], t[pre + "D"][20])
+            assert abs(d - a) <= 1e-6 * max(1.0, abs(a)) and abs(v - c) <= 1e-5 * max(1.0, abs(c))
+
+
+def test_v2_channel_events_finger_lands_on_a_cube_and_fingers_close_on_a_cube():
+    """BlockPhys v2: a gripper / finger channel follows the tabulated propagator until a contact acts on it.  Scripted
+    episodes drive both events: closed fingers descending onto cube 0 come to rest on its top face (grip z = cube z +
+    0.0385 + 0.025 - 0.02 while the target is below), open fingers lowered around cube 0 and closed stall on its faces
+    (q = 0.025 + 0.007 - 0.0079) -- and the cube stays where it was."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ref_callers_common as rc
+    ref = coracle.OracleVecEnv("BlocksTouch-v0", 64, seed=11)
+    ref.reset()
+    cube0 = ref.get_state()["blk_pos"][:, 0].copy()
+    rc.grasp_and_land_actions(ref)
+    st = ref.get_state()
+    land = (np.arange(64) % 2) == 0
+    assert np.mean(np.abs(st["grip_pos"][land, 2] - 0.5285) < 1e-6) > 0.9
+    assert np.mean(np.abs(st["finger_q"][~land] - 0.0241).max(axis=1) < 2e-4) > 0.9
+    assert np.mean(np.abs(st["blk_pos"][:, 0] - cube0).max(axis=1) < 2e-3) > 0.9
