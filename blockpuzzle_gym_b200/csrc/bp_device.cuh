@@ -77,6 +77,7 @@ template <> struct Cfg<6> { static constexpr int NB = 4, DIMO = 87, DIMG = 36; s
 // curriculum knobs handed to the kernels (host keeps the python doubles, fetch_env.py:340-348,404-415,561-563)
 struct Ranges {
     double obj_range, max_obj_range, wrong_obj_range;
+    int challenge;   // BlocksTouchChooseEnv(challenge=True), fetch_env.py:403,416,452-463 (bp_set_option "challenge")
 };
 
 // ---------------------------------------------------------------- Philox + elementary functions
@@ -1007,16 +1008,17 @@ __device__ __forceinline__ void randomize_objects(Env<Cfg<ID>::NB>& e, uint32_t 
             sample_around(e, ep, x0, y0, kMinBlockDist, r, x, y);
         } while (out_of_table(x, y) && ++it < kMaxSpawnAttempts);
         if (NB > 1) { e.px[NB > 1 ? 1 : 0] = (float)x; e.py[NB > 1 ? 1 : 0] = (float)y; }
-    } else if (ID == 4 || ID == 5) {  // BlocksTouchChoose fetch_env.py:448-517 (challenge=False)
+    } else if (ID == 4 || ID == 5) {  // BlocksTouchChoose fetch_env.py:448-517
         double r, wrong_r;
-        if (test) { r = rg.max_obj_range; wrong_r = 0.0; }
+        if (test || rg.challenge) { r = rg.max_obj_range; wrong_r = 0.0; }   // :452-454
         else { r = rg.obj_range; wrong_r = rg.wrong_obj_range; }
-        double max_wrong_r = rg.max_obj_range;
+        const double min_r = rg.challenge ? 0.15 : kMinBlockDist;             // :458-463
+        const double max_wrong_r = rg.challenge ? 0.04 : rg.max_obj_range;
         double bx, by, gx, gy, wx, wy;
         sample_blue(e, ep, r, bx, by);
         int it = 0;
         do {
-            sample_around(e, ep, bx, by, kMinBlockDist, r, gx, gy);
+            sample_around(e, ep, bx, by, min_r, r, gx, gy);
         } while (out_of_table(gx, gy) && ++it < kMaxSpawnAttempts);
         double cx = (bx + gx) / 2.0, cy = (by + gy) / 2.0;
         it = 0;

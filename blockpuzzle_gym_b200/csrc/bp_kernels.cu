@@ -450,6 +450,7 @@ struct bp_handle {
     float* d_stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
     cudaEvent_t ev = nullptr;       // orders the staging streams after the caller's stream
+    int challenge = 0;              // bp_set_option("challenge"): BlocksTouchChooseEnv(challenge=True), fetch_env.py:403,416
     int force_full = 0;             // bp_set_option("force_full_physics"): every env-step takes the full-physics pass
     int step_kernel = -1;           // bp_set_option("step_kernel"): -1 default (BP_STEP_KERNEL, else async), 0 async, 2 simple, 4 split
     // step-synchronous path (bp_split.cuh): per-step work lists and per-block statistics slots
@@ -460,7 +461,7 @@ struct bp_handle {
 };
 
 static Ranges ranges_of(const bp_handle* h) {
-    return Ranges{h->obj_range, h->max_obj_range, h->wrong_obj_range};
+    return Ranges{h->obj_range, h->max_obj_range, h->wrong_obj_range, h->challenge};
 }
 
 template <typename F>
@@ -906,6 +907,11 @@ int bp_increase_difficulty(bp_handle* h, int* max_reached) {
 int bp_set_option(bp_handle* h, const char* name, int value) {
     if (!h || !name) return fail(BP_ERR_INVALID_ARG, "null argument");
     if (strcmp(name, "force_full_physics") == 0) { h->force_full = value != 0; return BP_OK; }
+    if (strcmp(name, "challenge") == 0) {   // the `challenge` constructor argument of BlocksTouchChooseEnv (fetch_env.py:403,416)
+        if (h->env_id != 4 && h->env_id != 5) return fail(BP_ERR_INVALID_ARG, "challenge is an argument of BlocksTouchChooseEnv only");
+        h->challenge = value != 0;
+        return BP_OK;
+    }
     if (strcmp(name, "step_kernel") == 0) {   // -1 default, 0 async (slab-resident, K steps fused in one kernel), 2 simple, 4 split
         if (value != -1 && value != 0 && value != 2 && value != 4) return fail(BP_ERR_INVALID_ARG, "step_kernel must be -1, 0, 2 or 4");
         h->step_kernel = value;

@@ -88,7 +88,7 @@ class DictSpace:
 class VecBlocksEnv:
     """B independent gym_blocks envs of one registered id, resident on one B200."""
 
-    def __init__(self, env_name, num_envs, device=None, seed=0, env_index_offset=0):
+    def __init__(self, env_name, num_envs, device=None, seed=0, env_index_offset=0, challenge=False):
         self.L = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.BlockPuzzleError("blockpuzzle_gym_b200 needs a CUDA device (no CPU fallback)")
@@ -115,6 +115,13 @@ class VecBlocksEnv:
         check(self.L.bp_stats_ptr(self._h, C.byref(sp)))
         self._stats_ptr = sp.value
         self._goal = None
+        # `challenge`: the constructor argument of BlocksTouchChooseEnv (fetch_env.py:403,416); any other class of the
+        # reference would raise TypeError on the unexpected keyword
+        self.challenge = bool(challenge)
+        if self.challenge:
+            if "Choose" not in env_name:
+                raise TypeError("__init__() got an unexpected keyword argument 'challenge'")
+            self.set_option("challenge", 1)
         self.seed(seed)
 
     def __del__(self):
@@ -408,11 +415,11 @@ class GymBlocksEnv:
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 25}
     reward_range = (-float("inf"), float("inf"))
 
-    def __init__(self, env_name, device=None, seed=0, reward_type="sparse"):
+    def __init__(self, env_name, device=None, seed=0, reward_type="sparse", challenge=False):
         # reward_type: the registered kwarg (gym_blocks/__init__.py:9 ...); the reference stores it and never reads
         # it (fetch_env.py:72, appendix A8)
         self.reward_type = reward_type
-        self._vec = VecBlocksEnv(env_name, 1, device=device, seed=seed)
+        self._vec = VecBlocksEnv(env_name, 1, device=device, seed=seed, challenge=challenge)
         self.spec_id = env_name
         self._max_episode_steps = MAX_EPISODE_STEPS
         self._elapsed_steps = None

@@ -170,7 +170,11 @@ int bp_set_test(bp_handle* h, float* d_obs, float* d_ag, float* d_g, void* strea
  * (BlocksTouchChoose-v0 without curriculum: obj_range_step is never set, fetch_env.py:413-415,420). */
 int bp_increase_difficulty(bp_handle* h, int* max_reached);
 int bp_get_difficulty(const bp_handle* h, int* difficulty);           /* fetch_env.py:96-97 */
-/* measurement knobs (no reference counterpart).  "force_full_physics" != 0: every env-step runs the complete
+/* "challenge" (BlocksTouchChoose ids only; BP_ERR_INVALID_ARG otherwise): the `challenge` constructor argument of
+ * BlocksTouchChooseEnv (fetch_env.py:403,416) -- every spawn then uses max_obj_range, keeps the wrong block within 0.04 of
+ * the pair's centre and the pair at least 0.15 apart (fetch_env.py:452-463).  No tasks.py class sets it.
+ * Measurement knobs (no reference counterpart): "step_kernel" (-1 default, 0 async, 2 simple, 4 split);
+ * "force_full_physics" != 0: every env-step runs the complete
  * BlockPhys step (no quiet path) -- results are identical, only slower: the floor bench.py reports. */
 int bp_set_option(bp_handle* h, const char* name, int value);
 /* direct access to the curriculum knobs (obj_range, wrong_obj_range, max_obj_range) */

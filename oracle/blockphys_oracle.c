@@ -808,13 +808,14 @@ static void sample_blue(bpo_env* env, double r, double* x, double* y) {
     } while (out_of_table(*x, *y) && ++it < MAX_SPAWN_ATTEMPTS);
 }
 
-/* BlocksTouchChooseEnv._randomize_objects fetch_env.py:448-517 (challenge=False: tasks.py never sets it) */
+/* BlocksTouchChooseEnv._randomize_objects fetch_env.py:448-517; `challenge` (:403,416,452-463) is a constructor
+ * argument no tasks.py class sets -- bpo_env_set_challenge stands for constructing the env with challenge=True */
 static void randomize_choose(bpo_env* env, int test) {
     double r, wrong_r;
-    if (test) { r = env->max_obj_range; wrong_r = 0.0; }
+    if (test || env->challenge) { r = env->max_obj_range; wrong_r = 0.0; }   /* :452-454 */
     else { r = env->obj_range; wrong_r = env->wrong_obj_range; }
-    double min_r = MIN_BLOCK_DIST;
-    double max_wrong_r = env->max_obj_range;
+    double min_r = env->challenge ? 0.15 : MIN_BLOCK_DIST;                     /* :458-463 */
+    double max_wrong_r = env->challenge ? 0.04 : env->max_obj_range;
     int blue = 1, green = 0, wrong = 2; /* colours [GREEN, BLUE, GREY], :465-473 */
     double bx, by, gx, gy, wx, wy;
     sample_blue(env, r, &bx, &by);
@@ -1024,6 +1025,11 @@ int bpo_env_increase_difficulty(bpo_env* env) {
 int bpo_env_get_difficulty(const bpo_env* env) { return env->difficulty; } /* fetch_env.py:96-97 */
 double bpo_env_get_obj_range(const bpo_env* env) { return env->obj_range; }
 /* test hook (mirrors bp_set_ranges): direct write of the curriculum knobs */
+int bpo_env_set_challenge(bpo_env* env, int challenge) { /* fetch_env.py:403,416 */
+    if (env->env_id != BPO_BLOCKS_TOUCH_CHOOSE && env->env_id != BPO_BLOCKS_TOUCH_CHOOSE_CURRICULUM) return -1;
+    env->challenge = challenge != 0;
+    return 0;
+}
 void bpo_env_set_ranges(bpo_env* env, double obj_range, double wrong_obj_range) { env->obj_range = obj_range; env->wrong_obj_range = wrong_obj_range; }
 
 /* _step_callback fetch_env.py:148-167 */

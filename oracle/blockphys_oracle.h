@@ -115,6 +115,7 @@ typedef struct {
     uint32_t episode;
     uint32_t draws[2];
     uint32_t invalid_actions;  /* count of non-finite action components seen */
+    int32_t challenge;         /* BlocksTouchChooseEnv(challenge=True), fetch_env.py:403,416 */
 } bpo_env;
 
 /* geometry of the env ids */
@@ -152,6 +153,7 @@ int bpo_env_increase_difficulty(bpo_env* env);     /* 1 max reached, 0 not, -1 N
 int bpo_env_get_difficulty(const bpo_env* env);
 double bpo_env_get_obj_range(const bpo_env* env);
 void bpo_env_set_ranges(bpo_env* env, double obj_range, double wrong_obj_range); /* test hook, mirrors bp_set_ranges */
+int bpo_env_set_challenge(bpo_env* env, int challenge); /* BlocksTouchChooseEnv(challenge=...), fetch_env.py:403,416; -1 for other ids */
 void bpo_env_get_obs(const bpo_env* env, float* obs, float* ag, float* g);
 void bpo_env_get_state(const bpo_env* env, bpo_env_state* out);
 void bpo_env_set_state(bpo_env* env, const bpo_env_state* in);

@@ -94,6 +94,8 @@ def lib():
         L.bpo_env_get_obj_range.argtypes = [vp]
         L.bpo_env_get_obj_range.restype = C.c_double
         L.bpo_env_set_ranges.argtypes = [vp, C.c_double, C.c_double]
+        L.bpo_env_set_challenge.argtypes = [vp, C.c_int]
+        L.bpo_env_set_challenge.restype = C.c_int
         L.bpo_env_get_state.argtypes = [vp, vp]
         L.bpo_env_set_state.argtypes = [vp, vp]
         L.bpo_env_random_action.argtypes = [vp, vp]
@@ -194,6 +196,12 @@ class OracleVecEnv:
     def set_ranges(self, obj_range, wrong_obj_range=0.0):
         for i in range(self.n):
             self.L.bpo_env_set_ranges(self._env_ptr(i), float(obj_range), float(wrong_obj_range))
+
+    def set_challenge(self, challenge=True):
+        """BlocksTouchChooseEnv(challenge=True) (fetch_env.py:403,416): the two Choose ids only."""
+        for i in range(self.n):
+            if self.L.bpo_env_set_challenge(self._env_ptr(i), int(bool(challenge))) != 0:
+                raise TypeError("challenge is an argument of BlocksTouchChooseEnv only")
 
     def random_actions(self):
         a = np.zeros((self.n, 4), np.float32)

@@ -298,9 +298,12 @@ MAX_EPISODE_STEPS = 50  # __init__.py:10
 class BlocksEnvOracle:
     """One env of any registered id: BlocksEnv + its task subclass + the TimeLimit wrapper."""
 
-    def __init__(self, env_name):
+    def __init__(self, env_name, challenge=False):
         cfg = TASKS[env_name]
         self.cfg, self.kind, self.eid = cfg, cfg["kind"], cfg["eid"]
+        if challenge and cfg["kind"] != "choose":
+            raise TypeError("challenge is an argument of BlocksTouchChooseEnv only")   # fetch_env.py:403
+        self.challenge = challenge                              # fetch_env.py:416
         self.block_gripper = cfg["block_gripper"]
         self.max_num_blocks = cfg["nblocks"]
         self.obj_range = 0.15                                   # tasks.py:18
@@ -496,17 +499,20 @@ class BlocksEnvOracle:
                     break
             self.sim.set_obj_xy(1, xy)
         elif self.kind == "choose":                             # fetch_env.py:448-517
-            if test:
+            if test or self.challenge:                          # :452-463
                 r, wrong_r = self.max_obj_range, 0
             else:
                 r, wrong_r = self.obj_range, self.wrong_obj_range
-            max_wrong_r = self.max_obj_range
+            if self.challenge:
+                max_wrong_r, min_r = 0.04, 0.15
+            else:
+                min_r, max_wrong_r = MIN_BLOCK_DIST64, self.max_obj_range
             blocks = self.obj_colors[2:5]
             blue, green = blocks.index(BLUE), blocks.index(GREEN)
             wrong = [i for i in range(3) if i not in (blue, green)][0]
             pb = self._blue(r)
             self.sim.set_obj_xy(blue, pb)
-            pg = self._green(pb, r)
+            pg = self._green(pb, r, min_r)
             self.sim.set_obj_xy(green, pg)
             centre = (pb + pg) / 2.0
             it = 0
@@ -555,10 +561,10 @@ class BlocksEnvOracle:
             if not out_of_table64(xy) or it >= MAX_SPAWN_ATTEMPTS:
                 return xy
 
-    def _green(self, pb, r):                                    # fetch_env.py:488-494, 732-738
+    def _green(self, pb, r, min_r=MIN_BLOCK_DIST64):            # fetch_env.py:488-494, 732-738
         it = 0
         while True:
-            xy = self._around(pb, MIN_BLOCK_DIST64, r)
+            xy = self._around(pb, min_r, r)
             it += 1
             if not out_of_table64(xy) or it >= MAX_SPAWN_ATTEMPTS:
                 return xy
@@ -614,5 +620,5 @@ class BlocksEnvOracle:
         return np.array([f32(f32(f32(2.0) * u01(x)) - f32(1.0)) for x in w], f32)
 
 
-def make(env_name):
-    return BlocksEnvOracle(env_name)
+def make(env_name, challenge=False):
+    return BlocksEnvOracle(env_name, challenge=challenge)

@@ -466,6 +466,32 @@ def test_spawn_rejection_loop_cap(name, obj_range):
     _assert_state_equal(env, ref, "stepping from a capped spawn")
 
 
+@pytest.mark.parametrize("name", ["BlocksTouchChoose-v0", "BlocksTouchChooseCurriculum-v0"])
+def test_choose_env_challenge_argument(name):
+    """BlocksTouchChooseEnv(challenge=True) (fetch_env.py:403,416,452-463; pinned to the reference's own sampler in
+    tests/test_ref_pin.py): resets and auto-resets inside a fused launch spawn exactly like the oracle's."""
+    import blockpuzzle_gym_b200 as bpg
+    B = 512
+    env = bpg.make_vec(name, B, device=0, seed=9, challenge=True)
+    ref = coracle.OracleVecEnv(name, B, seed=9)
+    ref.set_challenge(True)
+    o = env.reset(); ro, rag, rg = ref.reset()
+    assert np.array_equal(o["observation"].cpu().numpy(), ro)
+    _assert_state_equal(env, ref, "after a challenge reset")
+    st = ref.get_state()
+    green, blue, wrong = (st["blk_pos"][:, k, :2].astype(np.float64) for k in range(3))
+    assert (np.linalg.norm(green - blue, axis=1) >= 0.15 - 1e-6).all()
+    assert (np.linalg.norm(wrong - (green + blue) / 2, axis=1) <= 0.04 + 1e-6).all()
+    out = env.step_fused(None, K=60, auto_reset=True, want_actions=True)       # crosses the auto-reset at step 50
+    acts = out["actions"].cpu().numpy()
+    for k in range(60):
+        obs, ag, r, s, _, _ = ref.step(acts[k], auto_reset=True)
+        assert np.array_equal(out["observation"][k].cpu().numpy(), obs), k
+    _assert_state_equal(env, ref, "after the fused launch")
+    with pytest.raises(TypeError):
+        bpg.make_vec("BlocksTouch-v0", 4, device=0, challenge=True)
+
+
 def test_gym_single_env_surface():
     """The object the reference gets from gym.make(env_name): reset/step/compute_reward/seed + TimeLimit."""
     import blockpuzzle_gym_b200 as bpg

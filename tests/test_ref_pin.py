@@ -105,6 +105,38 @@ def test_spawn_samplers_make_the_reference_rejection_decisions(name, resets, max
 
 
 @live
+@pytest.mark.parametrize("name", ["BlocksTouchChoose-v0", "BlocksTouchChooseCurriculum-v0"])
+def test_choose_env_with_challenge_true_matches_the_reference(name):
+    """R3 with `challenge=True` (fetch_env.py:403,416,452-463): no tasks.py class passes it, so the reference's own
+    `_randomize_objects` is run with the attribute its constructor would have set.  2000 resets: state records (spawned
+    positions, both draw counters) of reference, C oracle and Python oracle agree byte for byte, the blue / green pair is
+    >= 0.15 apart and the wrong block within 0.04 of their centre.  Other env classes do not take the argument."""
+    from oracle import gym_blocks_oracle as pyo
+    ref = rh.make(name, seed=5)
+    assert ref.unwrapped.challenge is False
+    ref.unwrapped.challenge = True
+    orc = coracle.OracleVecEnv(name, 1, seed=5)
+    orc.set_challenge(True)
+    py = pyo.make(name, challenge=True)
+    py.seed(5)
+    for i in range(2000):
+        ref.reset(); orc.reset()
+        a, b = rh.state_record(ref), orc.get_state()[0]
+        assert a.tobytes() == b.tobytes(), i
+        if i < 50:
+            py.reset()
+            for k in range(3):
+                assert np.array_equal(np.asarray(py.sim.obj_pos(k), np.float32), b["blk_pos"][k]), (i, k)
+        green, blue, wrong = b["blk_pos"][0][:2].astype(np.float64), b["blk_pos"][1][:2].astype(np.float64), b["blk_pos"][2][:2].astype(np.float64)
+        assert np.linalg.norm(green - blue) >= 0.15 - 1e-6
+        assert np.linalg.norm(wrong - (green + blue) / 2) <= 0.04 + 1e-6
+    with pytest.raises(TypeError):
+        coracle.OracleVecEnv("BlocksTouch-v0", 1, seed=5).set_challenge(True)
+    with pytest.raises(TypeError):
+        pyo.make("BlocksTouch-v0", challenge=True)
+
+
+@live
 def test_reference_compute_reward_goal_and_table_test_called_directly():
     """S6 / S7 / G0 straight from the reference module: BlocksEnv.compute_reward (fetch_env.py:135-143) against the
     oracle's bpo_compute_reward on random touch matrices, every id's _sample_goal (:260-273, :682-695) against
