@@ -38,6 +38,7 @@ def measure(emit=print, device=0, cpu_legs=True):
     ag = torch.cat([o0["achieved_goal"][None], out["achieved_goal"]], 0).transpose(0, 1).contiguous()
     g = env.goal()[:, None, :].expand(B_ep, T, dimg).contiguous()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sweep = torch.zeros(64 << 20, dtype=torch.float32, device=dev)   # 256 MB read after the flush: see timed()
     L = _lib.load()
     p = lambda t: C.c_void_p(t.data_ptr())
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -49,7 +50,11 @@ def measure(emit=print, device=0, cpu_legs=True):
             fn()
         ts = []
         for _ in range(reps):
+            # L2 flush: write a 256 MB buffer (2x the 126 MB L2), then read another 256 MB so that the lines the timed kernel
+            # evicts are clean -- otherwise it also pays for writing the flush's own dirty lines back to HBM (measured on
+            # Normalizer.update: 47 us after the write alone, 41 us after write + read sweep, 39 us after a read-only flush)
             flush.zero_()
+            sweep.sum()
             torch.cuda._sleep(400000)   # ~0.2 ms of GPU spin: the host enqueues the timed launch before the GPU gets there,
                                         # so the events bracket device time, not Python / ctypes call latency
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -199,20 +199,30 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < V; ++j) { s[j] = 0.0; q[j] = 0.0; }
     if (rr < rpi) {
-#pragma unroll 4
-        for (int64_t r = r0 + rr; r < r1; r += rpi) {
-            float v[V];
-            if constexpr (V == 4) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(x + r * ld + col0) + c);
-                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-            } else {
-                v[0] = __ldg(x + r * ld + col0 + c);
+        // U independent 128-bit loads are issued before the first float64 operation consumes one: the kernel is bound by
+        // memory latency (ncu, round 2: 28 long-scoreboard stall cycles per issued instruction at 32 warps / SM with the
+        // rolled loop), so the bytes in flight per thread set its bandwidth.  Rows past the end contribute exact zeros.
+        constexpr int U = V == 4 ? 8 : 4;
+        for (int64_t r = r0 + rr; r < r1; r += (int64_t)rpi * U) {
+            float v[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t ru = r + (int64_t)u * rpi;
+                if constexpr (V == 4) {
+                    const float4 t = ru < r1 ? __ldg(reinterpret_cast<const float4*>(x + ru * ld + col0) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u][0] = t.x; v[u][1] = t.y; v[u][2] = t.z; v[u][3] = t.w;
+                } else {
+                    v[u][0] = ru < r1 ? __ldg(x + ru * ld + col0 + c) : 0.f;
+                }
             }
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const double d = (double)clip_sym(v[j], clip);
-                s[j] += d;
-                q[j] += d * d;
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const double d = (double)clip_sym(v[u][j], clip);
+                    s[j] += d;
+                    q[j] += d * d;
+                }
             }
         }
     }
