@@ -173,11 +173,13 @@ __device__ __forceinline__ uint32_t finalize_at(const StepArgs& p, int64_t li, i
                                                 float* s_cub, float* s_grp, uint32_t* s_msc, uint32_t* s_bits) {
     using C = Cfg<ID>;
     constexpr int CS = 32 * E;
-    if (LEAN) {   // time-major rows, no done / goal rows: one row index serves every tensor
-        const int64_t row = (int64_t)(p.k0 + k) * p.B + li;
+    if (LEAN) {   // time-major rows, no done / goal rows: one row index serves every tensor.  launch_step hands this
+                  // instantiation pointers already advanced to the launch's first step (k0 = act_k0 = 0) and only launches whose
+                  // K * B fits 31 bits, so the row index is 32-bit arithmetic and every address one widening multiply-add
+        const uint32_t row = (uint32_t)k * (uint32_t)p.B + (uint32_t)li;
         return finalize_step<ID, CS, true>(contacts, s_cub + w, s_grp + w, s_msc + w, s_bits + (k * E + (w >> 5)), 1u << (w & 31), nullptr,
-                                     (k + 1 < p.K) ? reinterpret_cast<const float4*>(p.actions) + ((int64_t)(p.act_k0 + k + 1) * p.B + li) : nullptr,
-                                     nullptr, p.obs ? p.obs + row * C::DIMO : nullptr, p.ag ? p.ag + row * C::DIMG : nullptr);
+                                     (k + 1 < p.K) ? reinterpret_cast<const float4*>(p.actions) + (row + (uint32_t)p.B) : nullptr,
+                                     nullptr, p.obs ? p.obs + (uint64_t)row * C::DIMO : nullptr, p.ag ? p.ag + (uint64_t)row * C::DIMG : nullptr);
     }
     const int64_t row = step_row(p, k, li), orow = obs_row(p, k, li);
     return finalize_step<ID, CS, false>(contacts, s_cub + w, s_grp + w, s_msc + w, s_bits + (k * E + (w >> 5)), 1u << (w & 31),
@@ -192,7 +194,7 @@ __device__ __forceinline__ uint32_t finalize_at(const StepArgs& p, int64_t li, i
 template <int ID, bool LEAN>
 __device__ __forceinline__ float4 fetch_action(const uint32_t* __restrict__ st, const StepArgs& p, int64_t li, int k, int t) {
     constexpr int NF = num_fields<Cfg<ID>::NB>();
-    if (LEAN) return __ldg(reinterpret_cast<const float4*>(p.actions) + ((int64_t)(p.act_k0 + k) * p.B + li));
+    if (LEAN) return __ldg(reinterpret_cast<const float4*>(p.actions) + ((uint32_t)k * (uint32_t)p.B + (uint32_t)li));   // k0 = 0, 32-bit rows: see finalize_at
     float4 a4;
     if (p.actions) {  // the action tensor is always time-major [Ktot][B][4]
         a4 = __ldg(reinterpret_cast<const float4*>(p.actions) + ((int64_t)(p.act_k0 + k) * p.B + li));
@@ -238,7 +240,7 @@ __device__ __forceinline__ uint32_t try_quiet_step(uint32_t* __restrict__ st, co
     bool quiet = true;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        if (b < nb) {
+        if (!C::VAR || b < nb) {
             const float* bb = s_cub + (9 * b) * CS + w;
             quiet = quiet && cube_out_of_reach(bb[0], bb[CS], bb[2 * CS], bb[3 * CS], bb[4 * CS], lo, hi, qmax);
         }
@@ -372,7 +374,7 @@ __device__ __forceinline__ void slab_flush(uint32_t* __restrict__ st, const Step
             for (int k = 0; k < p.K; ++k) {
                 const uint32_t fail = (s_bits[k * E + e] >> lane) & 1u;
                 latch |= fail ^ 1u;
-                const int64_t row = LEAN ? (int64_t)(p.k0 + k) * p.B + li : step_row(p, k, li);
+                const int64_t row = LEAN ? (int64_t)((uint32_t)k * (uint32_t)p.B + (uint32_t)li) : step_row(p, k, li);
                 if (p.reward) store_reward(p.reward + row, fail);
                 if (p.success) p.success[row] = (float)latch;
                 t += 1;

@@ -171,6 +171,10 @@ __device__ __forceinline__ void bp_normal2(uint32_t w0, uint32_t w1, float& z0, 
 }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+// clamp between two NONZERO bounds (velocity caps, the mocap reach box): min(max(x, lo), hi) is the same value as clampf
+// for every non-NaN x (no signed-zero case), a NaN becomes lo on both sides of the parity check, and it is two FMNMX
+// instead of four compare / select instructions
+__device__ __forceinline__ float clampnz(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 // BlockPhys v1.1: the fused multiply-adds of the spec are written explicitly (the file is compiled
 // with -fmad=false, so nothing else is ever contracted)
 #define F(a, b, c) __fmaf_rn((a), (b), (c))
@@ -651,10 +655,10 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, GripStep& sb
         const float ox = col.scr(i, 0), oy = col.scr(i, 1), oz = col.scr(i, 2);
         same = same && __float_as_uint(b.x) == __float_as_uint(ox) && __float_as_uint(b.y) == __float_as_uint(oy) &&
                __float_as_uint(b.z) == __float_as_uint(oz);
-        b.vx = clampf((b.x - ox) * kInvH, -kVMax, kVMax);
-        b.vy = clampf((b.y - oy) * kInvH, -kVMax, kVMax);
-        b.vz = clampf((b.z - oz) * kInvH, -kVMax, kVMax);
-        b.w = clampf(col.scr(i, 3) * kInvH, -kWMax, kWMax);
+        b.vx = clampnz((b.x - ox) * kInvH, -kVMax, kVMax);
+        b.vy = clampnz((b.y - oy) * kInvH, -kVMax, kVMax);
+        b.vz = clampnz((b.z - oz) * kInvH, -kVMax, kVMax);
+        b.w = clampnz(col.scr(i, 3) * kInvH, -kWMax, kWMax);
         {
             const bool supd = (sup >> i & 1u) != 0u;
             const float sp2 = F(b.vx, b.vx, b.vy * b.vy);
@@ -680,9 +684,9 @@ template <bool BG>
 __device__ __forceinline__ void action_targets(const Grip& e, const float a[4], float m[3], float ctrl[2]) {
     // v1.3: product and sum rounded separately -- the reference's float32 `pos_ctrl *= 0.05` (fetch_env.py:175)
     // followed by upstream's float64 mocap_pos + pos_delta narrows to exactly this
-    m[0] = clampf(e.g[0] + a[0] * kPosScale, kWsXLo, kWsXHi);
-    m[1] = clampf(e.g[1] + a[1] * kPosScale, kWsYLo, kWsYHi);
-    m[2] = clampf(e.g[2] + a[2] * kPosScale, kGZMin, kWsZHi);
+    m[0] = clampnz(e.g[0] + a[0] * kPosScale, kWsXLo, kWsXHi);
+    m[1] = clampnz(e.g[1] + a[1] * kPosScale, kWsYLo, kWsYHi);
+    m[2] = clampnz(e.g[2] + a[2] * kPosScale, kGZMin, kWsZHi);
     float ga = BG ? 0.0f : a[3];
     ctrl[0] = clampf(e.q[0] + ga, 0.0f, kCtrlMax);
     ctrl[1] = clampf(e.q[1] + ga, 0.0f, kCtrlMax);
@@ -871,10 +875,10 @@ __device__ __forceinline__ bool substep_cubes_reg(Grip& e, GripSub& st, GripStep
         if (!VAR || i < nb) {
             same = same && __float_as_uint(q.x[i]) == __float_as_uint(q.ox[i]) && __float_as_uint(q.y[i]) == __float_as_uint(q.oy[i]) &&
                    __float_as_uint(q.z[i]) == __float_as_uint(q.oz[i]);
-            float vx = clampf((q.x[i] - q.ox[i]) * kInvH, -kVMax, kVMax);
-            float vy = clampf((q.y[i] - q.oy[i]) * kInvH, -kVMax, kVMax);
-            const float vz = clampf((q.z[i] - q.oz[i]) * kInvH, -kVMax, kVMax);
-            float w = clampf(q.dth[i] * kInvH, -kWMax, kWMax);
+            float vx = clampnz((q.x[i] - q.ox[i]) * kInvH, -kVMax, kVMax);
+            float vy = clampnz((q.y[i] - q.oy[i]) * kInvH, -kVMax, kVMax);
+            const float vz = clampnz((q.z[i] - q.oz[i]) * kInvH, -kVMax, kVMax);
+            float w = clampnz(q.dth[i] * kInvH, -kWMax, kWMax);
             const bool supd = (sup >> i & 1u) != 0u;
             const float sp2 = F(vx, vx, vy * vy);
             if (supd && sp2 > kFr * kFr) {
@@ -1155,7 +1159,7 @@ __device__ __forceinline__ void env_write_obs(const Env<Cfg<ID>::NB>& e, Store&&
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         constexpr int per = C::VAR ? 19 : 15;
-        const bool live = i < e.nb;
+        const bool live = !C::VAR || i < e.nb;   // only the Variation env has fewer live cubes than slots
         put(o + 0, live ? e.px[i] : 0.0f);
         put(o + 1, live ? e.py[i] : 0.0f);
         put(o + 2, live ? e.pz[i] : 0.0f);

@@ -559,7 +559,8 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
             const int e_sel = e_def;   // other E are only instantiated in the experiments build
             (void)e_env;
             // the lean instantiation serves the plain fused step (see step_kernel_async)
-            const bool lean = a.layout == 0 && a.actions && !a.actions_out && !a.done && !a.goal_out && !a.reset_obs && !a.reset_ag;
+            const bool lean = a.layout == 0 && a.actions && !a.actions_out && !a.done && !a.goal_out && !a.reset_obs && !a.reset_ag &&
+                              a.B * (int64_t)kMaxFused < (int64_t)1 << 31;   // 32-bit row indices inside the lean kernel
             auto go = [&](auto ec, auto lc) -> int {
                 constexpr int E = decltype(ec)::value;
                 constexpr bool LEAN = decltype(lc)::value;
@@ -584,6 +585,15 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                     c.K = (a.K - k0) < kMaxFused ? (a.K - k0) : kMaxFused;
                     c.k0 = a.k0 + k0;
                     c.act_k0 = a.act_k0 + k0;
+                    if (LEAN) {   // the lean kernel addresses rows from the launch's first step: advance the tensors, k0 = act_k0 = 0
+                        const int64_t r0 = (int64_t)c.k0 * a.B;
+                        c.actions = a.actions + (int64_t)c.act_k0 * a.B * 4;
+                        if (c.obs) c.obs = a.obs + r0 * Cfg<ID>::DIMO;
+                        if (c.ag) c.ag = a.ag + r0 * Cfg<ID>::DIMG;
+                        if (c.reward) c.reward = a.reward + r0;
+                        if (c.success) c.success = a.success + r0;
+                        c.k0 = 0; c.act_k0 = 0;
+                    }
                     step_kernel_async<ID, E, LEAN><<<nblk(a.B, A::CS), 32, A::SMEM + pad, s>>>(h->d_state, c);
                 }
                 return (int)BP_OK;

@@ -235,6 +235,10 @@ void bpo_sim_init(bpo_sim* sim, int env_id) {
 }
 
 static float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+/* clamp between two NONZERO bounds as min(max(x, lo), hi) (IEEE minNum / maxNum: a NaN becomes lo).  Same value as
+ * clampf for every non-NaN x -- no signed-zero case since neither bound is zero; two FMNMX instead of four
+ * compare / select instructions in the CUDA library (BlockPhys v2: velocity caps and the mocap reach box). */
+static float clampnz(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 /* BlockPhys v1.1+: the fused multiply-adds of the spec are written explicitly (single rounding) */
 #define F(a, b, c) fmaf((a), (b), (c))
 
@@ -242,9 +246,9 @@ static float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi 
  * mocap_pos and the two finger-actuator controls as float64.  BlockPhys narrows them to binary32,
  * keeps the mocap target inside the arm-reach box and the controls inside ctrlrange (2blocks.xml:40). */
 void bpo_sim_set_targets(bpo_sim* sim, const double mocap_pos[3], const double ctrl[2]) {
-    sim->m[0] = clampf((float)mocap_pos[0], WS_XLO, WS_XHI);
-    sim->m[1] = clampf((float)mocap_pos[1], WS_YLO, WS_YHI);
-    sim->m[2] = clampf((float)mocap_pos[2], GZ_MIN, WS_ZHI);
+    sim->m[0] = clampnz((float)mocap_pos[0], WS_XLO, WS_XHI);
+    sim->m[1] = clampnz((float)mocap_pos[1], WS_YLO, WS_YHI);
+    sim->m[2] = clampnz((float)mocap_pos[2], GZ_MIN, WS_ZHI);
     sim->ctrl[0] = clampf((float)ctrl[0], 0.0f, CTRL_MAX);
     sim->ctrl[1] = clampf((float)ctrl[1], 0.0f, CTRL_MAX);
 }
@@ -255,9 +259,9 @@ void bpo_sim_set_targets(bpo_sim* sim, const double mocap_pos[3], const double c
  * v1.3: the product and the sum are rounded separately, which is what the reference's float32
  * multiply followed by the float64 mocap_pos + pos_delta narrows to (v1.1-1.2 fused them). */
 void bpo_sim_set_action(bpo_sim* sim, const float a[4]) {
-    sim->m[0] = clampf(sim->g[0] + a[0] * POS_SCALE, WS_XLO, WS_XHI);
-    sim->m[1] = clampf(sim->g[1] + a[1] * POS_SCALE, WS_YLO, WS_YHI);
-    sim->m[2] = clampf(sim->g[2] + a[2] * POS_SCALE, GZ_MIN, WS_ZHI);
+    sim->m[0] = clampnz(sim->g[0] + a[0] * POS_SCALE, WS_XLO, WS_XHI);
+    sim->m[1] = clampnz(sim->g[1] + a[1] * POS_SCALE, WS_YLO, WS_YHI);
+    sim->m[2] = clampnz(sim->g[2] + a[2] * POS_SCALE, GZ_MIN, WS_ZHI);
     float ga = sim->block_gripper ? 0.0f : a[3]; /* fetch_env.py:179-180 */
     sim->ctrl[0] = clampf(sim->q[0] + ga, 0.0f, CTRL_MAX);
     sim->ctrl[1] = clampf(sim->q[1] + ga, 0.0f, CTRL_MAX);
@@ -603,8 +607,8 @@ static void sim_substep(bpo_sim* sim, step_base* sb) {
         b->vel[1] = (b->pos[1] - tmp[i].old[1]) * INV_H;
         b->vel[2] = (b->pos[2] - tmp[i].old[2]) * INV_H;
         b->w = tmp[i].dth * INV_H;
-        for (int k = 0; k < 3; ++k) b->vel[k] = clampf(b->vel[k], -VMAX, VMAX);
-        b->w = clampf(b->w, -WMAX, WMAX);
+        for (int k = 0; k < 3; ++k) b->vel[k] = clampnz(b->vel[k], -VMAX, VMAX);
+        b->w = clampnz(b->w, -WMAX, WMAX);
         if (tmp[i].supported) {
             float sp2 = F(b->vel[0], b->vel[0], b->vel[1] * b->vel[1]);
             if (sp2 <= FR * FR) {
