@@ -2,7 +2,7 @@
 //
 // One thread advances one env: the gripper in registers, the cubes in a private shared-memory
 // column; the kernels in bp_kernels.cu decide how envs are tiled over warps.
-// Arithmetic follows the BlockPhys v1 specification of DESIGN.md exactly (fp32,
+// Arithmetic follows the BlockPhys v2 specification of DESIGN.md section 3 exactly (fp32,
 // every operation individually rounded: compile with -fmad=false), so integer
 // state is bit-exact and float state bit-identical against the CPU oracle.
 //
@@ -214,7 +214,7 @@ __device__ __forceinline__ void sim_init(Env<NB>& e, bool tower) {
     e.contacts = 0;
 }
 
-// ---------------------------------------------------------------- BlockPhys v1: sim.step()
+// ---------------------------------------------------------------- BlockPhys v2: sim.step()
 // The hot physics is written as compact loops over one env's cubes held in a PRIVATE shared-memory
 // column (field f of cube b at p[(9*b+f)*STRIDE]; per-substep scratch behind it), the gripper in
 // registers.  Loops are deliberately not unrolled: the whole step must stay inside the instruction

@@ -1,7 +1,7 @@
 /*
  * blockphys_oracle.c -- CPU ORACLE (test infrastructure, NOT the product).
  * See blockphys_oracle.h for the parity status ("parity unpinned" for the
- * MuJoCo slot) and DESIGN.md for the BlockPhys v1 specification.
+ * MuJoCo slot) and DESIGN.md section 3 for the BlockPhys v2 specification.
  *
  * Reference files restated here (paths relative to /root/reference/gym_blocks):
  *   envs/robot_env.py:53-82      seed / step / reset order of operations
@@ -24,7 +24,7 @@
 #include <string.h>
 
 /* ======================================================================
- * BlockPhys v1 constants (DESIGN.md section "BlockPhys v1")
+ * BlockPhys constants
  * ====================================================================== */
 #define NSUB 20          /* tasks.py:16 n_substeps */
 #define H 0.002f         /* 2blocks.xml:4 timestep */
@@ -59,7 +59,7 @@
 #define WMAX 60.0f
 #define IINV 2400.0f     /* inverse yaw inertia / inverse mass of a cube, 6/a^2, a = 0.05 */
 #define POS_SCALE 0.05f  /* fetch_env.py:175 */
-#define WS_XLO 1.0f      /* arm reach box for the mocap target (BlockPhys v1) */
+#define WS_XLO 1.0f      /* arm reach box for the mocap target (BlockPhys) */
 #define WS_XHI 1.6f
 #define WS_YLO 0.35f
 #define WS_YHI 1.15f
@@ -191,7 +191,7 @@ void bpo_normal2(uint32_t w0, uint32_t w1, float* z0, float* z1) {
 }
 
 /* ======================================================================
- * BlockPhys v1: the sim.step() slot
+ * BlockPhys v2: the sim.step() slot
  * ====================================================================== */
 int bpo_pair_index(int o1, int o2) {
     if (o1 > o2) { int t = o1; o1 = o2; o2 = t; }

@@ -17,7 +17,7 @@
  * fixtures tests/golden/ref_*.npz otherwise.
  * The sim.step() slot itself stays "own spec": the reference delegates rigid-body
  * dynamics to MuJoCo (robot_env.py:60), absent from /root/reference and from this
- * image; it is filled by the "BlockPhys v1.3" model of DESIGN.md, which this file
+ * image; it is filled by the "BlockPhys v2" model of DESIGN.md, which this file
  * implements normatively.
  *
  * Dynamics arithmetic is IEEE-754 binary32, the spawn samplers binary64 (as the

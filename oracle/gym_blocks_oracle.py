@@ -8,7 +8,7 @@ reference tree and from this image).
 
 Structure follows the reference one function at a time (paths relative to
 /root/reference/gym_blocks), with its own numpy-float32 arithmetic, and plugs the
-BlockPhys v1.3 C model (oracle/blockphys_oracle.c, via ctypes -- the role mujoco_py
+BlockPhys v2 C model (oracle/blockphys_oracle.c, via ctypes -- the role mujoco_py
 plays in the reference) into the `sim` slot:
 
     RobotEnv.seed / step / reset        envs/robot_env.py:53-82
@@ -202,7 +202,7 @@ class _Contact:
 
 
 class BlockSim:
-    """BlockPhys v1 behind the handful of mujoco_py calls the reference makes."""
+    """BlockPhys behind the handful of mujoco_py calls the reference makes."""
 
     GEOMS = ["floor0", "robot0:r_gripper_finger_link", "robot0:l_gripper_finger_link", "table",
              "object0", "object1", "object2", "object3"]
@@ -347,7 +347,7 @@ class BlocksEnvOracle:
 
     def step(self, action):                                     # robot_env.py:57-69
         action = np.asarray(action, f32)
-        action = np.where(np.isnan(action), f32(0), action)     # flagged, not raised (BlockPhys v1)
+        action = np.where(np.isnan(action), f32(0), action)     # flagged, not raised (BlockPhys)
         action = np.clip(action, f32(-1), f32(1))
         self._set_action(action)
         self.sim.step()

@@ -1,6 +1,6 @@
 """GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on the
 same seeded inputs.  Bar: bit-exact for integer state (touch matrix, latch, counters, Philox
-draw counters) AND bit-identical fp32 for every float (BlockPhys v1 fixes the op order)."""
+draw counters) AND bit-identical fp32 for every float (the BlockPhys specification fixes the op order)."""
 import os
 
 import numpy as np

@@ -163,7 +163,7 @@ def test_python_oracle_equals_c_oracle(name):
 @pytest.mark.parametrize("name", coracle.ENV_IDS)
 def test_golden_fixture(name):
     """Fixtures written by tests/golden/make_golden.py from the oracle at the commit that froze
-    BlockPhys v1: guards the spec against silent drift (the reference itself has no vectors)."""
+    BlockPhys: guards the spec against silent drift (the reference itself has no vectors)."""
     path = os.path.join(GOLDEN, name + ".npz")
     z = np.load(path)
     env = coracle.OracleVecEnv(name, int(z["num_envs"]), seed=int(z["seed"]))
@@ -210,7 +210,7 @@ def test_her_relabel_semantics():
     assert np.array_equal(a["ep_idx"], out["ep_idx"][100:200])
 
 
-# ---------------------------------------------------------------- physics invariants of BlockPhys v1
+# ---------------------------------------------------------------- physics invariants of BlockPhys
 @pytest.mark.parametrize("name", coracle.ENV_IDS)
 def test_physics_invariants_under_random_actions(name):
     env = coracle.OracleVecEnv(name, 128, seed=5)
@@ -283,7 +283,7 @@ def test_set_test_returns_stale_observation():
 
 
 def test_scripted_push_makes_blocks_touch():
-    """The task is solvable in BlockPhys v1: a scripted straight push of cube 0 into cube 1 latches
+    """The task is solvable in BlockPhys: a scripted straight push of cube 0 into cube 1 latches
     is_success (reward -0.0 at the touching step) for most spawns."""
 
     def run(seed):
