@@ -38,7 +38,7 @@ struct Async {
     // yaw cache (ids with the register pass): the yaw observation of every cube, bp_atan2(s, c), kept as a tenth column
     // per cube behind the nine state columns and refreshed only when the cube may have turned (slab load, reset, full-
     // physics pass).  _get_obs evaluated it for every cube at every env-step: 5.6 % of the kernel's instructions incl. the
-    // division slow path, and 4 KB of the hot code.  One more KB of slab: 11 instead of 12 resident warps, measured neutral.
+    // division slow path, and 4 KB of the hot code.  One more KB of slab: 12 x (18 KB + 1 KB reserved) is exactly the SM's 228 KB.
     static constexpr bool YAW = REG_PASS;
     static constexpr int W_CUB = (9 * NB + (YAW ? NB : 0)) * CS;
     static constexpr int W_COL = REG_PASS ? 0 : Col<NB, CS, 32>::kScratch * 32;
