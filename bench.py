@@ -488,6 +488,8 @@ def run_ours(args):
             for d in bench_her.measure(emit=None, device=local, cpu_legs=False):
                 key = d["metric"] + ("_future_p_%g" % d["future_p"] if "future_p" in d else "")
                 her[key] = {"value": d["value"], "unit": d["unit"], "ms": d["ms"], "roofline": d["roofline"], "workload": d.get("config", {}).get("workload")}
+            her["_method"] = ("CUDA events around each launch, median of 20; L2 flushed before every timed launch by writing a 256 MB "
+                              "buffer and then reading another 256 MB (so the evicted lines are clean)")
             line["her"] = her
         if world == 1 and not args.no_cpu_baseline:
             v = cpu_baseline_single()

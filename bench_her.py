@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs[3]: HER relabel + batched compute_reward over a 1 Mi-transition replay batch
 (future_p = 0.8 from replay_k = 4, config.py:49-50; and 0.0 for replay_strategy='none'), plus the plain
-compute_reward kernel.  Prints one JSON line per measurement (CUDA events, L2 flushed between runs)."""
+compute_reward kernel.  Prints one JSON line per measurement (CUDA events, L2 flushed between runs: a 256 MB write followed by a 256 MB read sweep)."""
 import json
 import os
 import sys
