@@ -481,14 +481,14 @@ static int dispatch(int env_id, F&& f) {
 static inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 // BP_STEP_KERNEL = async (default) | split (bp_split.cuh) | simple (full physics for every env-step: the cross-check of the quiet path and
-// the scheduler); built with -DBP_EXPERIMENTS also duo | tiled
+// the scheduler)
 static int step_kernel_choice() {
     static const int v = [] {
         const char* e = getenv("BP_STEP_KERNEL");
         if (e && strcmp(e, "simple") == 0) return 2;
         if (e && strcmp(e, "async") == 0) return 0;
         if (e && strcmp(e, "split") == 0) return 4;
-        return 0;   // default: the slab-resident kernel (step_kernel_async); split measured 4.21e9 vs 4.50e9 env-steps/s
+        return 0;   // default: the slab-resident kernel (step_kernel_async); split measured 4.09e9 vs 5.59e9 env-steps/s (BlockPhys v2)
     }();
     return v;
 }
@@ -554,10 +554,7 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
             // envs per lane (tuning).  Measured at the 18 KB slab, resident warps in brackets: E = 2 [20] 2.22e9, 3 [15] 3.16e9,
             // 4 [12] 3.28e9, 5 [10] 3.23e9, 6 [8] 3.08e9 env-steps/s
             // per id (E = 4 / 3 / 2): GripperTouch 3.78 / 3.97 / 3.83e9, ToppleTower 1.32 / 1.34 / 1.22e9, Variation 1.42 / 1.46 / 1.41e9
-            static const int e_env = [] { const char* e = getenv("BP_ASYNC_E"); return e ? atoi(e) : 0; }();
-            const int e_def = (ID == 0 || ID == 2 || ID == 6) ? 3 : kAsyncE;
-            const int e_sel = e_def;   // other E are only instantiated in the experiments build
-            (void)e_env;
+            // (E is a build-time constant: -DBP_ASYNC_E=3 for sweeps.  BlockPhys v2 kernel, E = 3 [15 warps] / 4 [12]: 4.65 / 4.87e9)
             // the lean instantiation serves the plain fused step (see step_kernel_async)
             const bool lean = a.layout == 0 && a.actions && !a.actions_out && !a.done && !a.goal_out && !a.reset_obs && !a.reset_ag &&
                               a.B * (int64_t)kMaxFused < (int64_t)1 << 31;   // 32-bit row indices inside the lean kernel
