@@ -1014,8 +1014,11 @@ int bp_her_relabel(const float* d_ep_ag, const float* d_ep_g, int32_t B, int32_t
     if (B <= 0 || T <= 0 || dimg <= 0 || n < 0) return fail(BP_ERR_INVALID_ARG, "bad sizes");
     if (n == 0) return BP_OK;
     if (!d_ep_ag || !d_ep_g) return fail(BP_ERR_INVALID_ARG, "null episode store");
-    // the goal / reward subset of the transition sampler: same draw, same kernel (block-cooperative row gathers)
     if (dimg > 256) return fail(BP_ERR_INVALID_ARG, "dimg > 256 is not supported (the registered ids have dimg <= 36)");
+    // rows of 1 / 2 / 4 / 8 float4 chunks (dimg = 16: the BlocksTouch ids): the lane-cooperative kernel
+    const int rc = bp_her_relabel_coop(d_ep_ag, d_ep_g, B, T, dimg, n, future_p, seed, index_offset, d_ep_idx, d_t, d_future_t, d_ag2, d_g, d_r, stream);
+    if (rc != BP_ERR_NOT_IMPLEMENTED) return rc;
+    // otherwise the goal / reward subset of the transition sampler: same draw, same outputs (block-cooperative row gathers)
     return bp_her_sample(nullptr, nullptr, d_ep_g, d_ep_ag, nullptr, B, T, 1, 0, dimg, n, future_p, 0.0f, seed, index_offset,
                          d_ep_idx, d_t, d_future_t, nullptr, nullptr, nullptr, d_g, nullptr, d_ag2, d_r, nullptr, nullptr, stream);
 }

@@ -182,6 +182,61 @@ __global__ void __launch_bounds__(kSampleThreads) her_sample_kernel(const __grid
     }
 }
 
+// bp_her_relabel for rows of CPR float4 chunks (CPR = 1, 2, 4, 8; dimg = 16 -> 4): CPR lanes per transition.  Every lane of a
+// row group makes the same Philox draw (redundant, but shuffle-free and the kernel is bound by the random row reads), loads
+// ONE float4 of ag_2 = ag[t + 1] and of the goal row (the future ag when relabelled, else g[t]) -- a warp reads 32 / CPR
+// random 64-byte rows per tensor and instruction as whole sector pairs -- and stores its chunk of g' (and ag_2) coalesced.
+// The reward's dot product is accumulated in the reference's left-to-right order by handing the running sum from lane
+// to lane, exactly as compute_reward_coop_kernel does.  Same draws, same outputs as her_sample_kernel (the tests compare
+// both with the oracle); measured 54 -> see profiles/README.md: the thread-per-transition phase + block-cooperative
+// re-gather of the generic sampler was the cost, not the random reads (tools/gather_ceiling.cu: 35 us for this pattern).
+template <int CPR>
+__global__ void __launch_bounds__(256) her_relabel_coop_kernel(const float4* __restrict__ ep_ag, const float4* __restrict__ ep_g, const int B,
+                                                               const int T, const int64_t n, const float future_p, const uint32_t k0,
+                                                               const uint32_t k1, const int64_t index_offset, int32_t* __restrict__ ep_idx,
+                                                               int32_t* __restrict__ t_idx, int32_t* __restrict__ fut_t,
+                                                               float4* __restrict__ ag2_out, float4* __restrict__ g_out, float* __restrict__ r) {
+    const int64_t tid = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t i = tid / CPR;
+    const int chunk = (int)(threadIdx.x & (CPR - 1));
+    const bool live = i < n;   // a row group never straddles the end: the grid covers n * CPR rounded up to whole blocks
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+    int e = 0, t = 0, ft = 0;
+    bool her = false;
+    if (live) {
+        const uint64_t gi = (uint64_t)(i + index_offset);
+        const U4 w = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 3u, 0u, k0, k1);
+        e = (int)__umulhi(w.x, (uint32_t)B);                       // episode_idxs = randint(0, B)
+        t = (int)__umulhi(w.y, (uint32_t)T);                       // t_samples = randint(T)
+        her = u01(w.z) < future_p;                                 // uniform(size) < future_p
+        ft = t + 1 + (int)(u01(w.w) * (float)(T - t));             // t + 1 + (uniform * (T - t)).astype(int)
+        const int64_t ag_row = (int64_t)e * (T + 1) + t;
+        x = __ldg(ep_ag + (ag_row + 1) * CPR + chunk);             // ag_2 = ag[:, 1:]
+        y = her ? __ldg(ep_ag + ((int64_t)e * (T + 1) + ft) * CPR + chunk) : __ldg(ep_g + ((int64_t)e * T + t) * CPR + chunk);
+    }
+    int c = (y.x != 0.0f) + (y.y != 0.0f) + (y.z != 0.0f) + (y.w != 0.0f);
+    float d = 0.0f;
+#pragma unroll
+    for (int j = 0; j < CPR; ++j) {
+        const float prev = __shfl_up_sync(0xffffffffu, d, 1, CPR);
+        if (chunk == j) {
+            d = j == 0 ? 0.0f : prev;
+            d = d + x.x * y.x; d = d + x.y * y.y; d = d + x.z * y.z; d = d + x.w * y.w;
+        }
+    }
+#pragma unroll
+    for (int o = CPR / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o, CPR);
+    if (!live) return;
+    if (g_out) __stcs(g_out + i * CPR + chunk, y);
+    if (ag2_out) __stcs(ag2_out + i * CPR + chunk, x);
+    if (chunk == CPR - 1 && r) store_reward(r + i, d != (float)c);
+    if (chunk == 0) {
+        if (ep_idx) ep_idx[i] = e;
+        if (t_idx) t_idx[i] = t;
+        if (fut_t) fut_t[i] = her ? ft : -1;
+    }
+}
+
 // Normalizer.update(v): local_sum += v.sum(0), local_sumsq += (v ** 2).sum(0), local_count += v.shape[0]
 // x [n][dim] (row stride ld, first column col0: the Variation rule o[:, 1:] of ddpg.py:180-181) ->
 // acc [2 * dim + 1] double, added atomically.  A block of 256 threads walks a slab of rows_per_block rows;
@@ -328,6 +383,27 @@ __global__ void __launch_bounds__(256) trim_kernel(const float* __restrict__ o, 
 }  // namespace bp
 
 using namespace bp;
+
+// bp_her_relabel's fast path (see her_relabel_coop_kernel); returns BP_ERR_NOT_IMPLEMENTED when the shape does not qualify
+int bp_her_relabel_coop(const float* d_ep_ag, const float* d_ep_g, int32_t B, int32_t T, int32_t dimg, int64_t n, float future_p,
+                        uint64_t seed, int64_t index_offset, int32_t* d_ep_idx, int32_t* d_t, int32_t* d_future_t, float* d_ag2,
+                        float* d_g, float* d_r, void* stream) {
+    const int cpr = dimg / 4;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(d_ep_ag) | reinterpret_cast<uintptr_t>(d_ep_g) | reinterpret_cast<uintptr_t>(d_ag2) |
+                         reinterpret_cast<uintptr_t>(d_g);
+    if ((dimg & 3) != 0 || (cpr != 1 && cpr != 2 && cpr != 4 && cpr != 8) || (al & 15) != 0) return BP_ERR_NOT_IMPLEMENTED;
+    const unsigned blocks = (unsigned)((n * cpr + 255) / 256);
+    const float4 *a4 = reinterpret_cast<const float4*>(d_ep_ag), *g4 = reinterpret_cast<const float4*>(d_ep_g);
+    float4 *o2 = reinterpret_cast<float4*>(d_ag2), *og = reinterpret_cast<float4*>(d_g);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cpr == 1) her_relabel_coop_kernel<1><<<blocks, 256, 0, s>>>(a4, g4, B, T, n, future_p, k0, k1, index_offset, d_ep_idx, d_t, d_future_t, o2, og, d_r);
+    else if (cpr == 2) her_relabel_coop_kernel<2><<<blocks, 256, 0, s>>>(a4, g4, B, T, n, future_p, k0, k1, index_offset, d_ep_idx, d_t, d_future_t, o2, og, d_r);
+    else if (cpr == 4) her_relabel_coop_kernel<4><<<blocks, 256, 0, s>>>(a4, g4, B, T, n, future_p, k0, k1, index_offset, d_ep_idx, d_t, d_future_t, o2, og, d_r);
+    else her_relabel_coop_kernel<8><<<blocks, 256, 0, s>>>(a4, g4, B, T, n, future_p, k0, k1, index_offset, d_ep_idx, d_t, d_future_t, o2, og, d_r);
+    BP_CU(cudaGetLastError());
+    return BP_OK;
+}
 
 extern "C" {
 

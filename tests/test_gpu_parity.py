@@ -213,10 +213,13 @@ def test_compute_reward_matches_oracle_and_kats():
     assert bpg.compute_reward(np.zeros((0, 16), np.float32), np.zeros((0, 16), np.float32), None).shape == (0,)
 
 
-def test_her_relabel_matches_oracle():
+@pytest.mark.parametrize("name,dimg,n", [("BlocksTouch-v0", 16, 20000), ("BlocksTouch-v0", 16, 20001), ("ToppleTower-v0", 36, 5001), ("GripperTouch-v0", 9, 5000)])
+def test_her_relabel_matches_oracle(name, dimg, n):
+    """bp_her_relabel against the oracle: rows of 4 float4 chunks (dimg 16) take the lane-cooperative kernel
+    (her_relabel_coop_kernel; n = 20001 leaves a partial last block), dimg 36 / 9 the generic sampler kernel."""
     import blockpuzzle_gym_b200 as bpg
-    B, T, dimg = 300, 50, 16
-    env = bpg.make_vec("BlocksTouch-v0", B, device=0, seed=5)
+    B, T = 300, 50
+    env = bpg.make_vec(name, B, device=0, seed=5)
     o0 = env.reset()
     out = env.step_fused(None, K=T, auto_reset=False)
     ag = torch.cat([o0["achieved_goal"][None], out["achieved_goal"]], 0).transpose(0, 1).contiguous()  # [B,T+1,dimg]
@@ -224,7 +227,6 @@ def test_her_relabel_matches_oracle():
     for strategy, fp in (("future", 0.8), ("none", 0.0)):
         sampler = bpg.make_sample_her_transitions(strategy, 4, None, seed=77)
         assert abs(sampler.future_p - fp) < 1e-12
-        n = 20000
         tr = sampler(dict(ag=ag, g=g), n, index_offset=1000)
         ref = coracle.her_relabel(ag.cpu().numpy(), g.cpu().numpy(), n, fp, 77, 1000)
         for k in ("ep_idx", "t", "future_t", "ag_2", "g", "r"):
