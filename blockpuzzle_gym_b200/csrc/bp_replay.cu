@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) her_relabel_coop_kernel(const float4* __r
 // a thread always serves the same V columns (V = 4: 128-bit loads when rows keep 16-byte alignment), so its
 // partial sums stay in registers; one shared and one global atomic per column and block at the end.
 template <int V>
-__global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ x, int64_t n, int dim, int ld, int col0, float clip,
+__global__ void __launch_bounds__(256, 4) moments_kernel(const float* __restrict__ x, int64_t n, int dim, int ld, int col0, float clip,
                                                       int rows_per_block, double* acc) {
     const int chunks = dim / V;
     const int rpi = 256 / chunks;                       // row slots per block iteration (dim <= 256)
