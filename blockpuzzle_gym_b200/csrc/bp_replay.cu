@@ -297,26 +297,41 @@ __global__ void __launch_bounds__(256, 4) moments_kernel(const float* __restrict
 
 // policy_gradient/rollout.py:255-258: after step t, returns[t_] += gamma ** (t - t_) * r_t for t_ < t, with
 // returns[t] = r_t appended first.  So G[t_] = r[t_] + sum_{j >= 1} pw[j] * r[t_ + j], accumulated in that
-// order in float64 (pw[j] = gamma ** j as the host's Python float power).  A block stages the rewards of
-// kRetEpisodes episodes and the power table in shared memory (coalesced loads), then every thread produces
-// outputs (episode, t_) in address order (coalesced float64 stores); T <= kRetMaxT.
-constexpr int kRetEpisodes = 32, kRetMaxT = 128;
-__global__ void __launch_bounds__(256) discounted_returns_kernel(const float* __restrict__ r, int64_t B, int T, const double* __restrict__ pw,
+// order in float64 (pw[j] = gamma ** j as the host's Python float power): T - 1 - t_ dependent multiply-adds per output,
+// an O(T^2) triangle per episode that is kept for bit-exactness -- the kernel is bound by float64 issue, not by HBM.
+// A block stages the rewards of `eps` episodes (as float64) and the power table in shared memory (coalesced loads).
+// One thread produces the PAIR of outputs (t_, T - 1 - t_): together they are exactly T - 1 multiply-adds, so every
+// thread runs the same trip count and a warp executes no idle lane-iterations (with one output per thread a warp ran the
+// 45+ iterations of its longest chain for an average of 25: 0.79 ms per 1 Mi episodes; see profiles/README.md).  T <= kRetMaxT.
+constexpr int kRetMaxT = 128;
+__global__ void __launch_bounds__(256) discounted_returns_kernel(const float* __restrict__ r, int64_t B, int T, int eps, const double* __restrict__ pw,
                                                                  double* __restrict__ G) {
-    __shared__ float s_r[kRetEpisodes * kRetMaxT];
-    __shared__ double s_pw[kRetMaxT];
-    const int64_t b0 = (int64_t)blockIdx.x * kRetEpisodes;
-    const int nb = (int)((B - b0) < kRetEpisodes ? (B - b0) : kRetEpisodes);
+    extern __shared__ double s_ret[];          // [kRetMaxT] powers, then [eps][T] rewards
+    double* s_pw = s_ret;
+    double* s_r = s_ret + kRetMaxT;
+    const int64_t b0 = (int64_t)blockIdx.x * eps;
+    const int nb = (int)((B - b0) < eps ? (B - b0) : eps);
     const int total = nb * T;
-    for (int i = (int)threadIdx.x; i < total; i += 256) s_r[i] = __ldg(r + b0 * T + i);
+    for (int i = (int)threadIdx.x; i < total; i += 256) s_r[i] = (double)__ldg(r + b0 * T + i);
     for (int i = (int)threadIdx.x; i < T; i += 256) s_pw[i] = pw[i];
     __syncthreads();
-    for (int i = (int)threadIdx.x; i < total; i += 256) {
-        const int e = i / T, t0 = i - e * T;
-        const float* row = s_r + e * T;
-        double acc = (double)row[t0];
-        for (int t = t0 + 1; t < T; ++t) acc = acc + __dmul_rn(s_pw[t - t0], (double)row[t]);
-        G[b0 * T + i] = acc;
+    const int P = (T + 1) / 2;                 // output pairs per episode (an odd T pairs its middle output with itself)
+    for (int w = (int)threadIdx.x; w < nb * P; w += 256) {
+        const int e = w / P, t0 = w - e * P, t1 = T - 1 - t0;
+        const double* row = s_r + e * T;
+        const int len0 = T - 1 - t0;           // terms of output t0; output t1 has t0 of them
+        double acc = row[t0], out0 = 0.0;
+        int base = t0 + 1, jj = 0;
+#pragma unroll 4
+        for (int j = 0; j < T - 1; ++j) {
+            if (j == len0) { out0 = acc; acc = row[t1]; base = t1 + 1; jj = 0; }   // chain t0 is complete: start chain t1
+            acc = acc + __dmul_rn(s_pw[jj + 1], row[base + jj]);
+            ++jj;
+        }
+        double out1 = acc;
+        if (len0 == T - 1) { out0 = acc; out1 = row[t1]; }                         // t0 = 0: chain t1 = T - 1 has no terms
+        G[(b0 + e) * T + t0] = out0;
+        G[(b0 + e) * T + t1] = out1;
     }
 }
 
@@ -452,7 +467,11 @@ int bp_discounted_returns(const float* d_r, int64_t B, int32_t T, const double* 
     if (B < 0 || T <= 0 || T > kRetMaxT) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes (T must be in 1..128)");
     if (B == 0) return BP_OK;
     if (!d_r || !d_gamma_pow || !d_G) return bp_fail(BP_ERR_INVALID_ARG, "null pointer");
-    discounted_returns_kernel<<<(unsigned)((B + kRetEpisodes - 1) / kRetEpisodes), 256, 0, (cudaStream_t)stream>>>(d_r, B, T, d_gamma_pow, d_G);
+    // episodes per block: as many as 40 KB of shared memory hold (64 at most), so that the block's pairs fill its rounds
+    int eps = (int)((40 * 1024 - kRetMaxT * 8) / (T * 8));
+    eps = eps > 64 ? 64 : (eps < 1 ? 1 : eps);
+    const size_t smem = sizeof(double) * ((size_t)kRetMaxT + (size_t)eps * T);
+    discounted_returns_kernel<<<(unsigned)((B + eps - 1) / eps), 256, smem, (cudaStream_t)stream>>>(d_r, B, T, eps, d_gamma_pow, d_G);
     BP_CU(cudaGetLastError());
     return BP_OK;
 }

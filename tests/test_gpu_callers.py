@@ -127,9 +127,12 @@ def test_discounted_returns_bit_exact():
     G = bpg.discounted_returns(ep["r"], gamma)
     ref = co.discounted_returns(ep["r"].cpu().numpy().T, gamma).T          # the oracle is time-major like the reference loop
     assert G.dtype == torch.float64 and np.array_equal(G.cpu().numpy().view(np.uint64), np.ascontiguousarray(ref).view(np.uint64))
-    r = torch.randn(33, 7, device="cuda")                                   # arbitrary rewards, odd sizes
-    assert np.array_equal(bpg.discounted_returns(r, 0.9).cpu().numpy().view(np.uint64),
-                          np.ascontiguousarray(co.discounted_returns(r.cpu().numpy().T, 0.9).T).view(np.uint64))
+    # arbitrary rewards; odd and even T (the kernel pairs outputs t and T - 1 - t: an odd T has a self-paired middle),
+    # T = 1, 2, the maximum T = 128, and episode counts that leave a partial last block
+    for Bn, Tn in ((33, 7), (5, 1), (9, 2), (130, 50), (67, 128), (1, 51)):
+        r = torch.randn(Bn, Tn, device="cuda")
+        assert np.array_equal(bpg.discounted_returns(r, 0.9).cpu().numpy().view(np.uint64),
+                              np.ascontiguousarray(co.discounted_returns(r.cpu().numpy().T, 0.9).T).view(np.uint64)), (Bn, Tn)
 
 
 def test_trim_bit_exact():

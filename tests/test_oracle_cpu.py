@@ -352,3 +352,35 @@ def test_v2_channel_events_finger_lands_on_a_cube_and_fingers_close_on_a_cube():
     assert np.mean(np.abs(st["grip_pos"][land, 2] - 0.5285) < 1e-6) > 0.9
     assert np.mean(np.abs(st["finger_q"][~land] - 0.0241).max(axis=1) < 2e-4) > 0.9
     assert np.mean(np.abs(st["blk_pos"][:, 0] - cube0).max(axis=1) < 2e-3) > 0.9
+
+
+def test_quiet_path_interval_bound_contains_every_substep():
+    """The CUDA quiet path (quiet_gripper_step, bp_device.cuh) bounds the gripper / finger state over the 20 substeps of an
+    env-step by an interval product: state_n = target + A[n] d0 + B[n] v0 with A[n] in [Amin, Amax], B[n] in [Bmin, Bmax]
+    (all positive).  Checked here on the tables themselves, in the kernel's binary32 arithmetic, for 2*10^5 random start
+    states: every table-driven position lies inside [lo, hi] up to a few ulp -- far inside the kernel's 1e-5 guard."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_tables", os.path.join(root, "tools", "gen_blockphys_tables.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    t = {k: np.array(v, np.float32) for k, v in gen.tables().items()}
+    f32 = np.float32
+    rng = np.random.RandomState(3)
+    n = 200000
+    for pre, span_d, span_v, tgt in (("G", 0.06, 1.0, 1.3), ("F", 0.2, 2.0, 0.05)):
+        A, Bt = t[pre + "A"][1:], t[pre + "B"][1:]
+        assert (A > 0).all() and (Bt > 0).all()
+        amin, amax, bmin, bmax = A.min(), A.max(), Bt.min(), Bt.max()
+        d0 = rng.uniform(-span_d, span_d, n).astype(f32)
+        v0 = rng.uniform(-span_v, span_v, n).astype(f32)
+        v0[: n // 10] = 0
+        d0[n // 10: n // 5] = 0
+        m = np.full(n, tgt, f32)
+        lo = m + (np.minimum(amin * d0, amax * d0) + np.minimum(bmin * v0, bmax * v0))
+        hi = m + (np.maximum(amin * d0, amax * d0) + np.maximum(bmin * v0, bmax * v0))
+        assert lo.dtype == f32 and hi.dtype == f32
+        for k in range(20):
+            # the kernel's F(A, d0, F(B, v0, m)), evaluated in float64 and rounded: within an ulp of the binary32 FMA chain
+            g = (A[k].astype(np.float64) * d0 + (Bt[k].astype(np.float64) * v0 + m)).astype(f32)
+            assert (g >= lo - f32(1e-6)).all() and (g <= hi + f32(1e-6)).all(), (pre, k)
