@@ -298,41 +298,45 @@ __global__ void __launch_bounds__(256, 4) moments_kernel(const float* __restrict
 // policy_gradient/rollout.py:255-258: after step t, returns[t_] += gamma ** (t - t_) * r_t for t_ < t, with
 // returns[t] = r_t appended first.  So G[t_] = r[t_] + sum_{j >= 1} pw[j] * r[t_ + j], accumulated in that
 // order in float64 (pw[j] = gamma ** j as the host's Python float power): T - 1 - t_ dependent multiply-adds per output,
-// an O(T^2) triangle per episode that is kept for bit-exactness -- the kernel is bound by float64 issue, not by HBM.
-// A block stages the rewards of `eps` episodes (as float64) and the power table in shared memory (coalesced loads).
-// One thread produces the PAIR of outputs (t_, T - 1 - t_): together they are exactly T - 1 multiply-adds, so every
-// thread runs the same trip count and a warp executes no idle lane-iterations (with one output per thread a warp ran the
-// 45+ iterations of its longest chain for an average of 25: 0.79 ms per 1 Mi episodes; see profiles/README.md).  T <= kRetMaxT.
+// an O(T^2) triangle per episode that is kept for bit-exactness.  The kernel is bound by shared-memory wavefronts and
+// float64 issue, not by HBM, so the mapping minimises wavefronts per multiply-add:
+//   * a block owns 32 episodes, LANE = EPISODE: the rewards are staged transposed ([t][episode], float32), so the reward
+//     operand of a warp is one conflict-free wavefront and the power pw[j] is the same address for all lanes (a broadcast);
+//   * a warp produces the outputs t_ and T - 1 - t_ of its 32 episodes back to back: T - 1 multiply-adds per pair, the same
+//     for every pair, so the warps of a block finish together (the host picks the warp count that divides the pair count);
+//   * no lane ever idles inside a chain (all lanes of a warp share t_), and the outputs leave through a shared-memory
+//     stage as whole coalesced rows.
+// History (1 Mi episodes x T = 50): thread per output, rewards [episode][t] 0.79 ms; thread per output PAIR with float64
+// rewards 0.92 ms (4 wavefronts per multiply-add: slower); this form: see profiles/README.md.  T <= kRetMaxT.
 constexpr int kRetMaxT = 128;
-__global__ void __launch_bounds__(256) discounted_returns_kernel(const float* __restrict__ r, int64_t B, int T, int eps, const double* __restrict__ pw,
+__global__ void __launch_bounds__(256) discounted_returns_kernel(const float* __restrict__ r, int64_t B, int T, const double* __restrict__ pw,
                                                                  double* __restrict__ G) {
-    extern __shared__ double s_ret[];          // [kRetMaxT] powers, then [eps][T] rewards
+    extern __shared__ double s_ret[];                     // [kRetMaxT] powers | [32][T] output stage | [T][32] rewards (float)
     double* s_pw = s_ret;
-    double* s_r = s_ret + kRetMaxT;
-    const int64_t b0 = (int64_t)blockIdx.x * eps;
-    const int nb = (int)((B - b0) < eps ? (B - b0) : eps);
-    const int total = nb * T;
-    for (int i = (int)threadIdx.x; i < total; i += 256) s_r[i] = (double)__ldg(r + b0 * T + i);
-    for (int i = (int)threadIdx.x; i < T; i += 256) s_pw[i] = pw[i];
-    __syncthreads();
-    const int P = (T + 1) / 2;                 // output pairs per episode (an odd T pairs its middle output with itself)
-    for (int w = (int)threadIdx.x; w < nb * P; w += 256) {
-        const int e = w / P, t0 = w - e * P, t1 = T - 1 - t0;
-        const double* row = s_r + e * T;
-        const int len0 = T - 1 - t0;           // terms of output t0; output t1 has t0 of them
-        double acc = row[t0], out0 = 0.0;
-        int base = t0 + 1, jj = 0;
-#pragma unroll 4
-        for (int j = 0; j < T - 1; ++j) {
-            if (j == len0) { out0 = acc; acc = row[t1]; base = t1 + 1; jj = 0; }   // chain t0 is complete: start chain t1
-            acc = acc + __dmul_rn(s_pw[jj + 1], row[base + jj]);
-            ++jj;
-        }
-        double out1 = acc;
-        if (len0 == T - 1) { out0 = acc; out1 = row[t1]; }                         // t0 = 0: chain t1 = T - 1 has no terms
-        G[(b0 + e) * T + t0] = out0;
-        G[(b0 + e) * T + t1] = out1;
+    double* s_out = s_ret + kRetMaxT;
+    float* s_r = reinterpret_cast<float*>(s_out + 32 * T);
+    const int64_t b0 = (int64_t)blockIdx.x * 32;
+    const int nb = (int)((B - b0) < 32 ? (B - b0) : 32);
+    const int nthr = (int)blockDim.x, lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5), nwarp = nthr >> 5;
+    for (int i = (int)threadIdx.x; i < 32 * T; i += nthr) {   // coalesced read of [episode][t], transposed store
+        const int e = i / T, t = i - e * T;
+        s_r[t * 32 + e] = e < nb ? __ldg(r + b0 * T + i) : 0.0f;
     }
+    for (int i = (int)threadIdx.x; i < T; i += nthr) s_pw[i] = pw[i];
+    __syncthreads();
+    const int P = (T + 1) / 2;                            // output pairs (an odd T pairs its middle output with itself)
+    for (int p = warp; p < P; p += nwarp) {
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int t0 = half == 0 ? p : T - 1 - p;
+            double acc = (double)s_r[t0 * 32 + lane];
+#pragma unroll 4
+            for (int j = 1; j < T - t0; ++j) acc = acc + __dmul_rn(s_pw[j], (double)s_r[(t0 + j) * 32 + lane]);
+            s_out[lane * T + t0] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = (int)threadIdx.x; i < nb * T; i += nthr) G[b0 * T + i] = s_out[i];
 }
 
 // RolloutStudent.trim (policy_gradient/rollout.py:139-171): cut a batch of padded observations / touch
@@ -467,11 +471,17 @@ int bp_discounted_returns(const float* d_r, int64_t B, int32_t T, const double* 
     if (B < 0 || T <= 0 || T > kRetMaxT) return bp_fail(BP_ERR_INVALID_ARG, "bad sizes (T must be in 1..128)");
     if (B == 0) return BP_OK;
     if (!d_r || !d_gamma_pow || !d_G) return bp_fail(BP_ERR_INVALID_ARG, "null pointer");
-    // episodes per block: as many as 40 KB of shared memory hold (64 at most), so that the block's pairs fill its rounds
-    int eps = (int)((40 * 1024 - kRetMaxT * 8) / (T * 8));
-    eps = eps > 64 ? 64 : (eps < 1 ? 1 : eps);
-    const size_t smem = sizeof(double) * ((size_t)kRetMaxT + (size_t)eps * T);
-    discounted_returns_kernel<<<(unsigned)((B + eps - 1) / eps), 256, smem, (cudaStream_t)stream>>>(d_r, B, T, eps, d_gamma_pow, d_G);
+    // warps per block: the count in 4..8 that wastes the fewest pair slots (T = 50: 25 pairs -> 5 warps x 5 pairs)
+    const int P = (T + 1) / 2;
+    int nw = 8, best = 1 << 30;
+    for (int w = 8; w >= 4; --w) {
+        const int waste = ((P + w - 1) / w) * w - P;
+        if (waste < best) { best = waste; nw = w; }
+    }
+    const size_t smem = sizeof(double) * ((size_t)kRetMaxT + (size_t)32 * T) + sizeof(float) * (size_t)32 * T;
+    if (smem > 48 * 1024)   // T > 119: above the default dynamic shared-memory limit (the attribute is per device: set it on every such call)
+        BP_CU(cudaFuncSetAttribute(discounted_returns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    discounted_returns_kernel<<<(unsigned)((B + 31) / 32), 32 * nw, smem, (cudaStream_t)stream>>>(d_r, B, T, d_gamma_pow, d_G);
     BP_CU(cudaGetLastError());
     return BP_OK;
 }
