@@ -71,3 +71,28 @@ def grasp_and_land_actions(ref, steps=36):
         acts.append(a)
         outs.append(ref.step(a))
     return np.stack(acts), outs
+
+
+def homing_actions(ref, steps=100, seed=0):
+    """Contact-heavy closed loop on an OracleVecEnv of any id: the gripper homes in on a (per-env, per-phase) cube with noisy
+    steps, dives to table level and rams it, while the fingers open and close at random -- lifts, closing-undone events,
+    pushes off the table, cube-cube and tower contacts all occur.  Auto-reset at the TimeLimit.  Returns actions [steps][B][4]."""
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    B = ref.n
+    acts = []
+    for t in range(steps):
+        st = ref.get_state()
+        nb = np.maximum(st["num_objs"] - 2, 1)
+        target = (np.arange(B) + t // 17) % nb
+        cube = st["blk_pos"][np.arange(B), target]
+        gp = st["grip_pos"]
+        a = rng.uniform(-0.35, 0.35, size=(B, 4)).astype(np.float32)
+        d = (cube - gp) / 0.05
+        d[:, 2] = (np.where(t % 17 < 6, 0.56, 0.47) - gp[:, 2]) / 0.05          # hover, then dive
+        a[:, :3] += np.clip(d, -1, 1).astype(np.float32)
+        a[:, 3] = np.where(rng.rand(B) < 0.5, 1.0, -1.0)
+        a[rng.rand(B) < 0.02] *= 3.0                                               # some out-of-range actions (the clip)
+        acts.append(a)
+        ref.step(a, auto_reset=True)
+    return np.stack(acts)

@@ -449,6 +449,38 @@ def test_v2_channel_events_match_oracle_on_every_step_kernel():
         _assert_state_equal(e2, ref, f"after the land / grasp episode with {opt}")
 
 
+@pytest.mark.parametrize("name", ["BlocksTouch-v0", "GripperTouch-v0", "ToppleTower-v0", "BlocksTouchChoose-v0", "BlocksTouchVariation-v0"])
+def test_contact_heavy_homing_policy_matches_oracle(name):
+    """A contact-heavy closed loop on every pass form (register pass: 1-2 cubes; column pass: 3-4 cubes; fingers free and
+    blocked): the gripper homes in on a cube, dives and rams it while the fingers open and close at random
+    (tests/ref_callers_common.homing_actions: by step 90 every env has a turned cube and 20-70 % have pushed one off the
+    table).  120 fused steps with auto-reset: every observation, touch matrix, reward and latch and the final state records
+    are bit-identical to the oracle's; BlocksTouch-v0 also with the quiet path disabled and on the split kernels."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import ref_callers_common as rc
+    B, K = 512, 120
+    rec = coracle.OracleVecEnv(name, B, seed=3)
+    rec.reset()
+    acts = rc.homing_actions(rec, K)
+    a = torch.from_numpy(acts).cuda()
+    for opt in ({}, {"force_full_physics": 1}, {"step_kernel": 4}) if name == "BlocksTouch-v0" else ({},):
+        env, ref = _make(name, B, seed=3)
+        for k, v in opt.items():
+            env.set_option(k, v)
+        env.reset(); ref.reset(); env.stats_reset()
+        out = env.step_fused(a, auto_reset=True)
+        for t in range(K):
+            o, ag, r, s, _, _ = ref.step(acts[t], auto_reset=True)
+            assert np.array_equal(out["observation"][t].cpu().numpy().view(np.uint32), o.view(np.uint32)), (opt, t)
+            assert np.array_equal(out["achieved_goal"][t].cpu().numpy(), ag), (opt, t)
+            assert np.array_equal(out["reward"][t].cpu().numpy().view(np.uint32), r.view(np.uint32)), (opt, t)
+            assert np.array_equal(out["is_success"][t].cpu().numpy(), s), (opt, t)
+        _assert_state_equal(env, ref, f"after the homing episodes with {opt}")
+        st = env.stats()
+        assert st["episodes"] == 2 * B and st["worker_steps"] / st["steps"] > 0.3     # far more full-physics steps than random actions (0.1)
+
+
 @pytest.mark.parametrize("name,obj_range", [("GripperTouch-v0", 0.05), ("ToppleTower-v0", 0.06)])
 def test_spawn_rejection_loop_cap(name, obj_range):
     """the 10 000-attempt cap of the spawn loops.  With obj_range < 0.1 / sqrt(2) the reference's
