@@ -43,22 +43,35 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ src, const
 #pragma unroll
     for (int j = 0; j < V; ++j) { sum[j] = 0.0; sq[j] = 0.0; }
     if (rr < rpi) {
-#pragma unroll 4
-        for (int r = rr; r < rows; r += rpi) {   // independent rows: several loads in flight per thread
-            float v[V];
-            if constexpr (V == 4) {
-                const float4 x = __ldg(reinterpret_cast<const float4*>(src + s_off[r]) + c);
-                v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-            } else {
-                v[0] = __ldg(src + s_off[r] + c);
+        // U independent row loads are issued before the first one is consumed (a rolled / exit-checked loop leaves one
+        // load in flight per thread: the gathers are bound by memory latency, as moments_kernel was); rows past the end
+        // are predicated off
+        constexpr int U = 4;
+        for (int r = rr; r < rows; r += rpi * U) {
+            float v[U][V];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ru = r + u * rpi;
+                if constexpr (V == 4) {
+                    const float4 x = ru < rows ? __ldg(reinterpret_cast<const float4*>(src + s_off[ru]) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u][0] = x.x; v[u][1] = x.y; v[u][2] = x.z; v[u][3] = x.w;
+                } else {
+                    v[u][0] = ru < rows ? __ldg(src + s_off[ru] + c) : 0.f;
+                }
             }
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                v[j] = clip_sym(v[j], clip);
-                if (STATS) { const double d = (double)v[j]; sum[j] += d; sq[j] += d * d; }
+            for (int u = 0; u < U; ++u) {
+                const int ru = r + u * rpi;
+                if (ru < rows) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        v[u][j] = clip_sym(v[u][j], clip);
+                        if (STATS) { const double d = (double)v[u][j]; sum[j] += d; sq[j] += d * d; }
+                    }
+                    if constexpr (V == 4) reinterpret_cast<float4*>(dst + (int64_t)ru * dim)[c] = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                    else dst[(int64_t)ru * dim + c] = v[u][0];
+                }
             }
-            if constexpr (V == 4) reinterpret_cast<float4*>(dst + (int64_t)r * dim)[c] = make_float4(v[0], v[1], v[2], v[3]);
-            else dst[(int64_t)r * dim + c] = v[0];
         }
         if (STATS) {  // this thread's partial sums: slot [rr][2 * dim] of the block's table (no atomics)
 #pragma unroll
