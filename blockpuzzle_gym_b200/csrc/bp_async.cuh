@@ -336,10 +336,24 @@ __device__ __forceinline__ uint32_t slab_load(const uint32_t* __restrict__ st, c
         const int64_t li = wbase + w;
         const bool live = li < p.B;
         const uint32_t* q = st + p.env0 + (live ? li : 0);
+        // five / nine independent loads in flight per lane (fully rolled, every load waited for the one before: 144
+        // serial DRAM round trips per lane at the start of each CTA)
 #pragma unroll 1
-        for (int d = 0; d < 10; ++d) s_grp[d * CS + w] = __uint_as_float(q[(int64_t)d * p.stateB]);
+        for (int d0 = 0; d0 < 10; d0 += 5) {
+            uint32_t v[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) v[j] = q[(int64_t)(d0 + j) * p.stateB];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) s_grp[(d0 + j) * CS + w] = __uint_as_float(v[j]);
+        }
 #pragma unroll 1
-        for (int d = 0; d < 9 * NB; ++d) s_cub[d * CS + w] = __uint_as_float(q[(int64_t)(10 + d) * p.stateB]);
+        for (int d0 = 0; d0 < 9 * NB; d0 += 9) {
+            uint32_t v[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) v[j] = q[(int64_t)(10 + d0 + j) * p.stateB];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) s_cub[(d0 + j) * CS + w] = __uint_as_float(v[j]);
+        }
         if (Async<ID, E>::YAW) yaw_refresh<NB, CS>(s_cub + w);
         int f = 10 + 9 * NB;
         s_msc[w] = q[(int64_t)f * p.stateB]; ++f;                        // touch
