@@ -628,10 +628,13 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, GripStep& sb
         Blk b = col.load(i);
         const float ox = col.scr(i, 0), oy = col.scr(i, 1);
         float dth = col.scr(i, 3);
+        bool moved = false;   // collide_* return false when they left the cubes untouched: nothing to write back then
 #pragma unroll 1
-        for (int f = 0; f < 2; ++f) collide_finger_block(e, st, sb, n, f, b, ox, oy, dth, rotated, sup, contacts, i);
-        col.scr(i, 3) = dth;
-        col.store_pose(i, b);
+        for (int f = 0; f < 2; ++f) moved = collide_finger_block(e, st, sb, n, f, b, ox, oy, dth, rotated, sup, contacts, i) || moved;
+        if (moved) {
+            col.scr(i, 3) = dth;
+            col.store_pose(i, b);
+        }
     }
     // 4c. cube pairs
 #pragma unroll 1
@@ -640,9 +643,10 @@ __device__ __forceinline__ bool substep_cubes(Grip& e, GripSub& st, GripStep& sb
         for (int j = i + 1; j < nb; ++j) {
             Blk a = col.load(i), b = col.load(j);
             float adth = col.scr(i, 3), bdth = col.scr(j, 3);
-            collide_block_block(a, col.scr(i, 0), col.scr(i, 1), adth, b, col.scr(j, 0), col.scr(j, 1), bdth, rotated, sup, contacts, i, j);
-            col.scr(i, 3) = adth; col.scr(j, 3) = bdth;
-            col.store_pose(i, a); col.store_pose(j, b);
+            if (collide_block_block(a, col.scr(i, 0), col.scr(i, 1), adth, b, col.scr(j, 0), col.scr(j, 1), bdth, rotated, sup, contacts, i, j)) {
+                col.scr(i, 3) = adth; col.scr(j, 3) = bdth;
+                col.store_pose(i, a); col.store_pose(j, b);
+            }
         }
     }
     // 4d. fingers vs table

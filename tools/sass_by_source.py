@@ -51,6 +51,10 @@ def load(fn):
         m = re.match(r"^(?:static )?__(?:device|global)__.*?([A-Za-z_0-9]+)\s*\(", l) or re.match(r"^__device__ __forceinline__ \S+ ([A-Za-z_0-9]+)\(", l)
         if m and not l.startswith(" "):
             name = m.group(1)
+        else:   # member functions of the small structs (Col::load / store / scr ...)
+            m2 = re.match(r"^\s+__device__ __forceinline__ [^(]*?([A-Za-z_0-9]+)\s*\(", l)
+            if m2:
+                name = "member:" + m2.group(1)
         tbl.append(name)
     funcs[fn] = tbl
 agg = collections.OrderedDict()
