@@ -570,11 +570,16 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
                 }
                 // the kernel keeps the reward / success bits of at most kMaxFused steps on chip: split longer K
                 // reset-pass threshold | full-physics-pass threshold << 8 | fill rule (tuning knobs)
-                static const int tune = [] {
+                constexpr int kPassMin = ID == 0 ? 3 : ((ID == 4 || ID == 5) ? 16 : 28);   // see the sweep quoted below
+                static const int tune = [pm = kPassMin] {
                     const char* r = getenv("BP_RESET_MIN"); const char* q = getenv("BP_PASS_MIN");
                     const char* fr = getenv("BP_FILL_RULE");   // margin of the fill-comparison pass trigger, -1: off
                     const int frv = fr ? atoi(fr) : 8;
-                    return (r ? atoi(r) : 32) | ((q ? atoi(q) : 28) << 8) | (frv >= 0 ? (1 << 16) | (frv << 17) : 0);   // measured (round 2, lean kernel): reset 4 / 32 -> 4.33 / 4.48e9 at pass 24; pass 20 / 24 / 28 -> 4.44 / 4.48 / 4.46e9 (every reset pass streams ~12 KB of cold code through the instruction cache); BlockPhys v2 kernel: pass 16 / 20 / 24 / 28 / 32 -> 4.48 / 4.74 / 4.86 / 4.92 / 4.84e9
+                    // per-id pass threshold (sweep of round 2, tools/sweep_ids_thresholds*.sh): GripperTouch-v0's passes are cheap (one cube, two finger
+                    // slots) and rare (3.6 % of env-steps), so waiting for a full warp only stretches the chain of the warp's hardest env:
+                    // 28 / 16 / 8 / 4 / 3 / 2 / 1 -> 4.38 / 4.49 / 5.08 / 7.32 / 8.04 / 7.75 / 6.55e9; the Choose ids (3 cubes): 28 / 20 / 16 / 12 / 8 ->
+                    // 1.88 / 1.96 / 1.99 / 1.93 / 1.74e9; ToppleTower / Variation: flat from 16 to 28
+                    return (r ? atoi(r) : 32) | ((q ? atoi(q) : pm) << 8) | (frv >= 0 ? (1 << 16) | (frv << 17) : 0);   // measured (round 2, lean kernel): reset 4 / 32 -> 4.33 / 4.48e9 at pass 24; pass 20 / 24 / 28 -> 4.44 / 4.48 / 4.46e9 (every reset pass streams ~12 KB of cold code through the instruction cache); BlockPhys v2 kernel: pass 16 / 20 / 24 / 28 / 32 -> 4.48 / 4.74 / 4.86 / 4.92 / 4.84e9
                 }();
                 for (int k0 = 0; k0 < a.K; k0 += kMaxFused) {
                     StepArgs c = a;
@@ -597,7 +602,10 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
             };
             using T_ = std::true_type; using F_ = std::false_type;
             auto go_e = [&](auto ec) -> int { return lean ? go(ec, T_()) : go(ec, F_()); };
-            int r = go_e(std::integral_constant<int, ((ID == 0 || ID == 2 || ID == 6) ? 3 : kAsyncE)>());
+#ifndef BP_E_ID0
+#define BP_E_ID0 3
+#endif
+            int r = go_e(std::integral_constant<int, (ID == 0 ? BP_E_ID0 : ((ID == 2 || ID == 6) ? 3 : kAsyncE))>());
             if (r != BP_OK) return r;
         }
         return (int)BP_OK;
