@@ -115,7 +115,42 @@ __device__ __forceinline__ void store_row(float* __restrict__ dst, Gen&& gen) {
         // neighbouring envs still need out of L2
         for (int j = 0; j < W / 4; ++j) __stcs(d4 + j, make_float4(row[4 * j], row[4 * j + 1], row[4 * j + 2], row[4 * j + 3]));
     } else {
+#ifdef BP_SCALAR_ROWS
         gen([&](int c, float v) { dst[c] = v; });
+#else
+        // Rows that are not 16-byte multiples (25 / 9, 55 / 25, 87 floats) start at any 4-byte alignment, a different one in
+        // every lane.  Written float by float they were W separate 4-byte requests per lane to the L2 (ncu, GripperTouch-v0:
+        // 28 written sectors per env-step for 5 sectors' worth of bytes, mio_throttle + short scoreboard the top stalls; Choose:
+        // the L2 at 57 % of its peak).  Here every lane writes `h` floats up to its next 16-byte boundary, then 128-bit stores
+        // from the row shifted left by `h` in registers (two select stages), then the tail: W / 4 + 10 store instructions
+        // (seven of them predicated scalars) and 2 W selects instead of W stores.
+        float row[W + 3];
+        gen([&](int c, float v) { row[c] = v; });
+        row[W] = 0.0f; row[W + 1] = 0.0f; row[W + 2] = 0.0f;
+        const unsigned h = (4u - ((unsigned)(reinterpret_cast<uintptr_t>(dst) >> 2) & 3u)) & 3u;
+        if (h > 0) __stcs(dst, row[0]);
+        if (h > 1) __stcs(dst + 1, row[1]);
+        if (h > 2) __stcs(dst + 2, row[2]);
+        float t[W + 2], u[W + 4];
+#pragma unroll
+        for (int i = 0; i < W + 2; ++i) t[i] = (h & 1u) ? row[i + 1] : row[i];
+#pragma unroll
+        for (int i = 0; i < W; ++i) u[i] = (h & 2u) ? t[i + 2] : t[i];     // u[i] = row[i + h]
+        u[W] = 0.0f; u[W + 1] = 0.0f; u[W + 2] = 0.0f; u[W + 3] = 0.0f;
+        constexpr int NV = (W - 3) / 4;                                    // 128-bit stores every alignment has
+        float* d = dst + h;
+        float4* d4 = reinterpret_cast<float4*>(d);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) __stcs(d4 + j, make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]));
+        const int rem = W - 4 * NV - (int)h;                               // 0 .. 6 floats left
+        constexpr int T0 = 4 * NV;
+        if (W - T0 >= 4 && rem >= 4) __stcs(d4 + NV, make_float4(u[T0], u[T0 + 1], u[T0 + 2], u[T0 + 3]));
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            if (rem < 4 && l < rem) __stcs(d + T0 + l, u[T0 + l]);
+            if (W - T0 > 4 + l) { if (rem >= 4 && l < rem - 4) __stcs(d + T0 + 4 + l, u[T0 + 4 + l]); }
+        }
+#endif
     }
 }
 

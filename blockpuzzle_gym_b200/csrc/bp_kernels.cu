@@ -605,7 +605,10 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
 #ifndef BP_E_ID0
 #define BP_E_ID0 3
 #endif
-            int r = go_e(std::integral_constant<int, (ID == 0 ? BP_E_ID0 : ((ID == 2 || ID == 6) ? 3 : kAsyncE))>());
+#ifndef BP_E_CHOOSE
+#define BP_E_CHOOSE kAsyncE
+#endif
+            int r = go_e(std::integral_constant<int, (ID == 0 ? BP_E_ID0 : ((ID == 2 || ID == 6) ? 3 : ((ID == 4 || ID == 5) ? BP_E_CHOOSE : kAsyncE)))>());
             if (r != BP_OK) return r;
         }
         return (int)BP_OK;
