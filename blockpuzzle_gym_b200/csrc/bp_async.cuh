@@ -110,9 +110,22 @@ __device__ __forceinline__ void store_row(float* __restrict__ dst, Gen&& gen) {
         float row[W];
         gen([&](int c, float v) { row[c] = v; });
         float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
         // streaming stores (evict-first): the 15.6 GB of output rows of a launch must not push the action rows the
         // neighbouring envs still need out of L2
+#ifndef BP_NO_STG256
+        if constexpr (W % 8 == 0) {
+            // rows of whole 32-byte sectors (40 / 16 floats): one 256-bit store per sector (sm_100: STG.E.256) when the
+            // caller's tensor is 32-byte aligned -- half the store instructions, and no sector is written in two halves
+            if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+#pragma unroll
+                for (int j = 0; j < W / 8; ++j)
+                    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j), "f"(row[8 * j]), "f"(row[8 * j + 1]),
+                                 "f"(row[8 * j + 2]), "f"(row[8 * j + 3]), "f"(row[8 * j + 4]), "f"(row[8 * j + 5]), "f"(row[8 * j + 6]), "f"(row[8 * j + 7]) : "memory");
+                return;
+            }
+        }
+#endif
+#pragma unroll
         for (int j = 0; j < W / 4; ++j) __stcs(d4 + j, make_float4(row[4 * j], row[4 * j + 1], row[4 * j + 2], row[4 * j + 3]));
     } else {
 #ifdef BP_SCALAR_ROWS
