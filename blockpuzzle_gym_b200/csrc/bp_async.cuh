@@ -104,7 +104,9 @@ __device__ __noinline__ void reset_env_slab(uint32_t* __restrict__ st, const Ste
 }
 
 // write a row of W floats generated by `gen(put)` to global memory (128-bit stores when rows are 16-byte multiples)
-template <int W, class Gen>
+// A32: the caller guarantees a 32-byte aligned tensor (the lean kernel: launch_step checks it), so rows of whole sectors
+// need no run-time alignment test and no 128-bit fallback in the hot code.
+template <int W, bool A32 = false, class Gen>
 __device__ __forceinline__ void store_row(float* __restrict__ dst, Gen&& gen) {
     if constexpr (W % 4 == 0) {
         float row[W];
@@ -116,7 +118,7 @@ __device__ __forceinline__ void store_row(float* __restrict__ dst, Gen&& gen) {
         if constexpr (W % 8 == 0) {
             // rows of whole 32-byte sectors (40 / 16 floats): one 256-bit store per sector (sm_100: STG.E.256) when the
             // caller's tensor is 32-byte aligned -- half the store instructions, and no sector is written in two halves
-            if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+            if (A32 || (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
 #pragma unroll
                 for (int j = 0; j < W / 8; ++j)
                     asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 8 * j), "f"(row[8 * j]), "f"(row[8 * j + 1]),
@@ -208,9 +210,9 @@ __device__ __noinline__ uint32_t finalize_step(uint32_t contacts, float* cub, fl
         float yw[NB];
 #pragma unroll
         for (int b = 0; b < NB; ++b) yw[b] = YAW ? cub[(9 * NB + b) * CS] : 0.0f;
-        store_row<C::DIMO>(obs_row_p, [&](auto&& put) { env_write_obs<ID>(e, put, YAW ? yw : nullptr); });
+        store_row<C::DIMO, LEAN>(obs_row_p, [&](auto&& put) { env_write_obs<ID>(e, put, YAW ? yw : nullptr); });
     }
-    if (ag_row_p) store_row<C::DIMG>(ag_row_p, [&](auto&& put) { env_write_ag<ID>(touch_now, touch_ever, put); });
+    if (ag_row_p) store_row<C::DIMG, LEAN>(ag_row_p, [&](auto&& put) { env_write_ag<ID>(touch_now, touch_ever, put); });
     return (fail ? 1u : 0u) | (done ? 2u : 0u) | ((done && succ) ? 4u : 0u);
 }
 

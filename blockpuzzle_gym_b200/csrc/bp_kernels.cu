@@ -557,7 +557,8 @@ static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
             // (E is a build-time constant: -DBP_ASYNC_E=3 for sweeps.  BlockPhys v2 kernel, E = 3 [15 warps] / 4 [12]: 4.65 / 4.87e9)
             // the lean instantiation serves the plain fused step (see step_kernel_async)
             const bool lean = a.layout == 0 && a.actions && !a.actions_out && !a.done && !a.goal_out && !a.reset_obs && !a.reset_ag &&
-                              a.B * (int64_t)kMaxFused < (int64_t)1 << 31;   // 32-bit row indices inside the lean kernel
+                              a.B * (int64_t)kMaxFused < (int64_t)1 << 31 &&   // 32-bit row indices inside the lean kernel
+                              ((reinterpret_cast<uintptr_t>(a.obs) | reinterpret_cast<uintptr_t>(a.ag)) & 31) == 0;   // ... which writes 32-byte-multiple rows with unchecked 256-bit stores
             auto go = [&](auto ec, auto lc) -> int {
                 constexpr int E = decltype(ec)::value;
                 constexpr bool LEAN = decltype(lc)::value;
@@ -804,7 +805,7 @@ int bp_rollout_step(bp_handle* h, int t, const float* d_actions, float* d_o, flo
     return launch_step(h, a, (cudaStream_t)stream);
 }
 
-static inline size_t align4(size_t nfloats) { return (nfloats + 3) & ~(size_t)3; }   // sub-buffers start on 16 bytes (float4 row stores)
+static inline size_t align4(size_t nfloats) { return (nfloats + 7) & ~(size_t)7; }   // sub-buffers start on 32 bytes (128- / 256-bit row stores)
 
 int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, float* h_ag, float* h_reward,
                  float* h_success, int auto_reset, void* stream) {
@@ -818,7 +819,7 @@ int bp_step_host(bp_handle* h, const float* h_actions, int K, float* h_obs, floa
     if (chunk > h->B) chunk = h->B;
     chunk &= ~(int64_t)127;
     if (chunk < 128) chunk = h->B < 128 ? h->B : 128;
-    const size_t need = per_env * (size_t)chunk + 5 * 16;   // + the alignment padding of the five sub-buffers
+    const size_t need = per_env * (size_t)chunk + 5 * 32;   // + the alignment padding of the five sub-buffers
     if (h->stage_bytes < need) {
         for (int i = 0; i < 2; ++i) {
             if (h->d_stage[i]) cudaFree(h->d_stage[i]);
