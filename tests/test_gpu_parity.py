@@ -347,6 +347,30 @@ def test_step_fused_reallocates_mismatched_output_buffers():
     assert out4["reward"].shape == (6, 100) and out4["reward"].is_contiguous()
 
 
+@pytest.mark.parametrize("name", ["BlocksTouch-v0", "GripperTouch-v0"])
+def test_step_fused_into_output_tensors_that_are_only_16_byte_aligned(name):
+    """The lean kernel writes 32-byte-multiple rows with unchecked 256-bit stores, so launch_step only takes it for 32-byte
+    aligned output tensors (bp_kernels.cu: launch_step).  Views that start 16 bytes into an allocation must fall back to the
+    general instantiation (run-time alignment test, 128-bit stores) and give the same bits."""
+    B, K = 1001, 7
+    env, _ = _make(name, B, seed=11)
+    env2, _ = _make(name, B, seed=11)
+    env.reset(); env2.reset()
+    g = torch.Generator().manual_seed(5)
+    a = (torch.rand(K, B, 4, generator=g) * 2 - 1).cuda()
+    want = env.step_fused(a, auto_reset=True)
+    out = {}
+    for k, shp in (("observation", (K, B, env2.dimo)), ("achieved_goal", (K, B, env2.dimg))):
+        n = K * B * shp[2]
+        raw = torch.empty(n + 8, dtype=torch.float32, device="cuda")
+        v = raw[4:4 + n].view(*shp)
+        assert v.data_ptr() % 32 == 16 and v.is_contiguous()
+        out[k] = v
+    got = env2.step_fused(a, auto_reset=True, out=out)
+    assert got["observation"].data_ptr() == out["observation"].data_ptr()
+    for k in ("observation", "achieved_goal", "reward", "is_success"):
+        assert torch.equal(got[k].view(torch.int32), want[k].view(torch.int32)), k
+
 @pytest.mark.parametrize("name,test", [("BlocksTouch-v0", False), ("BlocksTouchCurriculum-v0", True), ("ToppleTower-v0", False),
                                        ("BlocksTouchVariation-v0", False)])
 def test_closed_loop_collector_matches_stepwise_oracle(name, test):
