@@ -122,7 +122,10 @@ int bp_reset(bp_handle* h, const uint8_t* d_mask, float* d_obs, float* d_ag, flo
  *   auto_reset != 0: an env that finishes step T = 50 is reset inside the kernel
  *              after its outputs are written; its fresh reset observation goes to
  *              d_reset_obs [B][dimo] / d_reset_ag [B][dimg] (nullable).
- * Any output pointer may be NULL (that output is skipped). */
+ * Any output pointer may be NULL (that output is skipped).
+ * Alignment: every tensor must be 16-byte aligned; with d_obs and d_ag 32-byte
+ * aligned (any cudaMalloc / torch allocation) the plain fused step takes its
+ * fastest instantiation (256-bit row stores), otherwise the general one. */
 int bp_step(bp_handle* h, const float* d_actions, int K, float* d_obs, float* d_ag, float* d_reward,
             float* d_success, uint8_t* d_done, int auto_reset, float* d_reset_obs, float* d_reset_ag,
             float* d_actions_out, void* stream);
