@@ -541,6 +541,11 @@ static int launch_step_split(bp_handle* h, StepArgs& a, cudaStream_t s) {
 }
 
 static int launch_step(bp_handle* h, StepArgs& a, cudaStream_t s) {
+    // rows are read and written with 128-bit accesses: a tensor that is not 16-byte aligned would be a sticky device fault
+    if ((reinterpret_cast<uintptr_t>(a.actions) | reinterpret_cast<uintptr_t>(a.obs) | reinterpret_cast<uintptr_t>(a.ag) |
+         reinterpret_cast<uintptr_t>(a.goal_out) | reinterpret_cast<uintptr_t>(a.reset_obs) | reinterpret_cast<uintptr_t>(a.reset_ag) |
+         reinterpret_cast<uintptr_t>(a.actions_out)) & 15)
+        return fail(BP_ERR_INVALID_ARG, "step tensors must be 16-byte aligned");
     if ((h->step_kernel >= 0 ? h->step_kernel : step_kernel_choice()) == 4) return launch_step_split(h, a, s);
     static const size_t pad = [] { const char* e = getenv("BP_SMEM_PAD"); return e ? (size_t)atoi(e) : (size_t)0; }();  // occupancy experiments
     int rc = dispatch(h->env_id, [&](auto id) {

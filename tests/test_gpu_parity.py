@@ -370,6 +370,14 @@ def test_step_fused_into_output_tensors_that_are_only_16_byte_aligned(name):
     assert got["observation"].data_ptr() == out["observation"].data_ptr()
     for k in ("observation", "achieved_goal", "reward", "is_success"):
         assert torch.equal(got[k].view(torch.int32), want[k].view(torch.int32)), k
+    # 4 bytes into an allocation: refused (the rows are written with 128-bit stores), not a device fault
+    from blockpuzzle_gym_b200._lib import BlockPuzzleError
+    raw = torch.empty(K * B * env2.dimo + 8, dtype=torch.float32, device="cuda")
+    bad = {"observation": raw[1:1 + K * B * env2.dimo].view(K, B, env2.dimo)}
+    with pytest.raises(BlockPuzzleError, match="16-byte aligned"):
+        env2.step_fused(a, auto_reset=True, out=bad)
+    torch.cuda.synchronize()
+    env2.step_fused(a, auto_reset=True)   # the handle and the context are still usable
 
 @pytest.mark.parametrize("name,test", [("BlocksTouch-v0", False), ("BlocksTouchCurriculum-v0", True), ("ToppleTower-v0", False),
                                        ("BlocksTouchVariation-v0", False)])
