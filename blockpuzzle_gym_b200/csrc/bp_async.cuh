@@ -133,12 +133,12 @@ __device__ __forceinline__ void store_row(float* __restrict__ dst, Gen&& gen) {
 #ifdef BP_SCALAR_ROWS
         gen([&](int c, float v) { dst[c] = v; });
 #else
-        // Rows that are not 16-byte multiples (25 / 9, 55 / 25, 87 floats) start at any 4-byte alignment, a different one in
+        // Rows that are not 16-byte multiples (25 / 9, 55 / 25, 70, 87 floats) start at any 4-byte (70: 8-byte) alignment, a different one in
         // every lane.  Written float by float they were W separate 4-byte requests per lane to the L2 (ncu, GripperTouch-v0:
         // 28 written sectors per env-step for 5 sectors' worth of bytes, mio_throttle + short scoreboard the top stalls; Choose:
         // the L2 at 57 % of its peak).  Here every lane writes `h` floats up to its next 16-byte boundary, then 128-bit stores
         // from the row shifted left by `h` in registers (two select stages), then the tail: W / 4 + 10 store instructions
-        // (seven of them predicated scalars) and 2 W selects instead of W stores.
+        // (up to nine of them predicated scalars: three head, six tail slots) and 2 W selects instead of W stores.
         float row[W + 3];
         gen([&](int c, float v) { row[c] = v; });
         row[W] = 0.0f; row[W + 1] = 0.0f; row[W + 2] = 0.0f;
